@@ -1,0 +1,37 @@
+// Compile-mode glue.  The per-lane solver logic in rti_core.cuh is written once; it is compiled
+//   * by nvcc for sm_100a as the product (the only shipped path), and
+//   * by g++ with -DNMPC_HOST_EMUL *only* inside tests/host_emul/ as a lane-by-lane emulation
+//     used to debug the kernels in the GPU-less build container.  The emulation is test
+//     infrastructure: nothing in the product library or the Python package can reach it.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define NMPC_HD __host__ __device__ __forceinline__
+#define NMPC_D __device__ __forceinline__
+#else
+#define NMPC_HD inline
+#define NMPC_D inline
+#endif
+
+namespace nmpc {
+
+NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
+constexpr int LANES = 32;     // instances per tile = lanes per warp
+constexpr int NSTAGE = 80;    // N: scripts/<m>/common.py:5-9 (tf_ini=2.0, freq=40)
+
+// warp-wide "does any lane still want this sweep"; per-lane emulation on the host
+#if defined(__CUDA_ARCH__)
+#define NMPC_ANY(pred) (__any_sync(0xffffffffu, (pred)))
+#else
+#define NMPC_ANY(pred) (pred)
+#endif
+
+}  // namespace nmpc

@@ -1,0 +1,61 @@
+// TEST INFRASTRUCTURE ONLY.  Lane-by-lane CPU emulation of the CUDA per-lane logic in
+// nmpc_nav_control_b200/csrc/rti_core.cuh, compiled by g++ with -DNMPC_HOST_EMUL.  It exists so
+// the kernels' arithmetic can be checked against the oracle in the GPU-less build container;
+// it is never linked into the product library and the Python package cannot load it.
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+#include "../../nmpc_nav_control_b200/csrc/rti_core.cuh"
+
+using namespace nmpc;
+
+template <class M>
+static int run(int B, const double* W, const double* We, const double* lbx, const double* ubx,
+               const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+               const double* x0bar, const double* yref, int nyref, const double* We_inst,
+               double* x, double* u, int* status, int* iters, double* stats)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
+    std::vector<double> lti(NSTAGE * 4 * NV);
+    for (int k = 0; k < NSTAGE; k++) {
+        double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
+        S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+    }
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt};
+    std::vector<double> tile(R::tile_doubles);
+    for (int i = 0; i < B; i++) {
+        std::fill(tile.begin(), tile.end(), 0.0);
+        const int lane = i % LANES;
+        double* base = tile.data() + lane;
+        double* xi = x + (size_t)i * (NSTAGE + 1) * NX;
+        double* ui = u + (size_t)i * NSTAGE * NU;
+        const double* yi = yref + (size_t)i * (NSTAGE + 1) * nyref;
+        const double* wei = We_inst ? We_inst + (size_t)i * NX : We;
+        for (int k = 0; k <= NSTAGE; k++)
+            S::linearize_stage(k, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU, xi + (k < NSTAGE ? k + 1 : k) * NX,
+                               yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei, base + (size_t)k * R::NF * LANES);
+        typename S::LaneStats st;
+        S::qp_ipm_lane(base, tb, wei, *o, true, st);
+        status[i] = st.status; iters[i] = st.iter;
+        if (stats) { for (int q = 0; q < 4; q++) stats[i * 8 + q] = st.res[q]; stats[i * 8 + 4] = st.mu; stats[i * 8 + 5] = st.lin_res; stats[i * 8 + 6] = st.cond_fallbacks; }
+        if (st.status == 0 || st.status == 1)
+            for (int k = 0; k <= NSTAGE; k++)
+                S::step_stage(k, base + (size_t)k * R::NF * LANES, x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
+    }
+    return 0;
+}
+
+extern "C" int emul_rti(int model, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                        const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                        const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                        double* x, double* u, int* status, int* iters, double* stats)
+{
+    switch (model) {
+        case 0: return run<DiffModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
+        case 1: return run<Omni4Model>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
+        case 2: return run<TricModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
+    }
+    return -1;
+}
