@@ -1,0 +1,118 @@
+/*
+ * nmpc_b200.h — batched C ABI of the B200-native SQP-RTI solver (libnmpc_b200.so).
+ *
+ * This is the NEW batched entry point the north star asks for; the reference has no analogue
+ * (its caller solves one OCP per `{m}_acados_solve`, src/nmpc_nav_control/NMPCNavControlDiff.cpp:142).
+ * The closest upstream shape is acados' `{m}_acados_batch_solve(capsule**, int*, int)`.
+ * The single-instance acados-compatible ABI the reference's C++ controller binds is declared
+ * in include/acados_solver_{diff2amr,omni4amr,tric3amr}.h and include/acados_c/ocp_nlp_interface.h
+ * and is implemented on top of the functions below with batch = 1.
+ *
+ * Conventions: plain C, no exceptions, int return (0 = ok, <0 = NMPC_E_*).  "host" pointers
+ * are caller-owned and copied synchronously; "device" pointers are caller-owned CUDA device
+ * memory on the solver's device.  Device batches are structure-of-arrays with the instance
+ * index fastest: a[stage][component][instance].
+ */
+#ifndef NMPC_B200_H
+#define NMPC_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMPC_N 80                       /* scripts/<m>/common.py:5-9: N = ceil(tf_ini * freq) */
+
+enum { NMPC_MODEL_DIFF = 0, NMPC_MODEL_OMNI4 = 1, NMPC_MODEL_TRIC = 2 };
+
+/* per-instance status = acados status codes */
+enum { NMPC_SUCCESS = 0, NMPC_NAN_DETECTED = 1, NMPC_MAXITER = 2, NMPC_MINSTEP = 3, NMPC_QP_FAILURE = 4 };
+
+enum {
+    NMPC_E_ARG = -1,        /* bad argument / unsupported option                          */
+    NMPC_E_CUDA = -2,       /* CUDA runtime error (message via nmpc_last_error)           */
+    NMPC_E_NODEVICE = -3,   /* no CUDA device: there is no CPU fallback                   */
+    NMPC_E_CAPACITY = -4    /* batch larger than the capacity given at creation           */
+};
+
+/* interior-point options; defaults restate acados' PARTIAL_CONDENSING_HPIPM settings
+ *  */
+typedef struct {
+    double mu0, alpha_min, res_g_max, res_b_max, res_d_max, res_m_max;
+    double reg_prim, lam_min, t_min, tau_min, thr0;
+    int iter_max, cond_pred_corr;
+} nmpc_ipm_opts;
+
+typedef struct nmpc_solver nmpc_solver;
+
+typedef struct { int nx, nu, np, ny, nyn, nbx, nbu, n; } nmpc_dims_t;
+
+int nmpc_dims(int model, nmpc_dims_t* out);
+void nmpc_default_opts(nmpc_ipm_opts* o);
+const char* nmpc_last_error(void);
+
+/* One solver = one model on one device with room for `max_batch` instances.  Tables start at
+ * the code-generation defaults of config/nmpc_nav_control_acados_models.yaml (what
+ * `{m}_acados_create` yields, NMPCNavControlDiff.cpp:10-12); the iterate starts at x_k = default
+ * x0 (0,0,pi,0,..), u = 0. */
+int nmpc_create(int model, int max_batch, int device, nmpc_solver** out);
+int nmpc_destroy(nmpc_solver* s);
+
+/* stage-wise tables shared by all instances (host pointers).  Any pointer may be NULL = keep.
+ *   W_diag [N][ny]  diagonal of W in y order [x;u]   (ocp_nlp_cost_model_set(i,"W"), Diff.cpp:68-71)
+ *   We_diag [nx]    diagonal of W_e                   (ocp_nlp_cost_model_set(N,"W"), Diff.cpp:72-73)
+ *   lbx/ubx [N][nbx] row k = stage k+1                (constraints_model_set(i,"lbx"/"ubx"), Diff.cpp:49-56)
+ *   lbu/ubu [N][nbu] stages 0..N-1                    (constraints_model_set(i,"lbu"/"ubu"), Diff.cpp:58-65)
+ *   p [N][np]                                         ({m}_acados_update_params, Diff.cpp:44-46)  */
+int nmpc_set_weights(nmpc_solver* s, const double* W_diag, const double* We_diag);
+int nmpc_set_bounds(nmpc_solver* s, const double* lbx, const double* ubx, const double* lbu, const double* ubu);
+int nmpc_set_params(nmpc_solver* s, const double* p);
+int nmpc_set_opts(nmpc_solver* s, const nmpc_ipm_opts* o);
+int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o);
+
+/* the persisted iterate (x [N+1][nx][cap], u [N][nu][cap], device, SoA with leading dim cap =
+ * max_batch).  reset: zero it ({m}_acados_reset, Diff.cpp:177-181). */
+int nmpc_iterate_device(nmpc_solver* s, double** d_x, double** d_u, int* leading_dim);
+int nmpc_reset(nmpc_solver* s);
+/* same, enqueued on `stream` (cudaStream_t, NULL = the default stream) without host sync */
+int nmpc_reset_async(nmpc_solver* s, void* stream);
+/* instance-major host copies: x [B][N+1][nx], u [B][N][nu] */
+int nmpc_set_iterate_host(nmpc_solver* s, int B, const double* x, const double* u);
+int nmpc_get_iterate_host(nmpc_solver* s, int B, double* x, double* u);
+
+/* ---- the batched entry point: one SQP-RTI iteration of B independent OCPs ------------------
+ * All pointers are DEVICE pointers, SoA with leading dimension B:
+ *   d_x0bar [nx][B]            measured initial state          (stage-0 lbx = ubx, Diff.cpp:96-101)
+ *   d_yref  [N+1][nyref][B]    nyref = 3 (pose, rest 0) or ny  (cost_model_set(i,"yref"), Diff.cpp:121-124);
+ *                              the terminal row uses its first nx entries
+ *   d_We    [nx][B] or NULL    per-instance terminal weights   (the diff wrapper's W_e switch, Diff.cpp:127-139)
+ *   d_x, d_u                   iterate in/out; NULL = the solver's own persisted iterate
+ *   d_status [B] (int)         acados status per instance
+ *   d_qp_iter [B] (int)        interior-point iterations per instance
+ *   d_stats [8][B] or NULL     res_g,res_b,res_d,res_m, mu, lin_res, cond_fallbacks, qp_status
+ * Asynchronous on `stream` (cudaStream_t; NULL = the default stream); no host synchronisation inside. */
+int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref,
+                          const double* d_We, double* d_x, double* d_u, int ldxu,
+                          int* d_status, int* d_qp_iter, double* d_stats, void* stream);
+
+/* ---- host-buffer call (what a controller process would bind): instance-major host arrays ---
+ *   x0bar [B][nx], yref [B][N+1][nyref], We [B][nx] or NULL   -> copied H2D and transposed on device
+ *   u0 [B][nu], x1 [B][nx], status [B], qp_iter [B]            <- copied D2H (what run() reads, Diff.cpp:151-169)
+ * Uses and updates the solver's persisted iterate.  Synchronous. */
+int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
+                        double* u0, double* x1, int* status, int* qp_iter);
+
+/* timing of the last nmpc_rti_solve_* call on this solver, measured with CUDA events on its
+ * stream: ms[0] = K1+K2 linearise, ms[1] = K3 QP, ms[2] = K4 step, ms[3] = total incl. copies */
+int nmpc_last_timing(nmpc_solver* s, double* ms4);
+/* number of kernel launches issued by the last solve call */
+int nmpc_last_launches(const nmpc_solver* s);
+
+/* tiny device benchmark used by bench.py to measure the fp64 FMA peak (roofline denominator);
+ * returns achieved TFLOP/s */
+double nmpc_dfma_peak_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

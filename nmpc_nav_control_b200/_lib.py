@@ -1,0 +1,75 @@
+"""ctypes binding of libnmpc_b200.so (the C ABI in include/nmpc_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present, loading /
+creating a solver raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libnmpc_b200.so")
+
+# every symbol include/nmpc_b200.h declares
+SYMBOLS = [
+    "nmpc_dims", "nmpc_default_opts", "nmpc_last_error", "nmpc_create", "nmpc_destroy",
+    "nmpc_set_weights", "nmpc_set_bounds", "nmpc_set_params", "nmpc_set_opts", "nmpc_get_opts",
+    "nmpc_iterate_device", "nmpc_reset", "nmpc_reset_async", "nmpc_set_iterate_host", "nmpc_get_iterate_host",
+    "nmpc_rti_solve_device", "nmpc_rti_solve_host", "nmpc_last_timing", "nmpc_last_launches",
+    "nmpc_dfma_peak_tflops",
+]
+
+
+class IpmOpts(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("mu0", "alpha_min", "res_g_max", "res_b_max", "res_d_max", "res_m_max",
+                 "reg_prim", "lam_min", "t_min", "tau_min", "thr0")] + \
+               [("iter_max", C.c_int), ("cond_pred_corr", C.c_int)]
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nx", "nu", "np", "ny", "nyn", "nbx", "nbu", "n")]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m nmpc_nav_control_b200.build` "
+                "(nvcc, sm_100a). This package has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for s in SYMBOLS:
+            getattr(lib, s)
+        lib.nmpc_last_error.restype = C.c_char_p
+        lib.nmpc_dfma_peak_tflops.restype = C.c_double
+        lib.nmpc_dfma_peak_tflops.argtypes = [C.c_int, C.c_int]
+        lib.nmpc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.nmpc_destroy.argtypes = [C.c_void_p]
+        vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p
+        lib.nmpc_set_weights.argtypes = [vp, dp, dp]
+        lib.nmpc_set_bounds.argtypes = [vp, dp, dp, dp, dp]
+        lib.nmpc_set_params.argtypes = [vp, dp]
+        lib.nmpc_set_opts.argtypes = [vp, C.POINTER(IpmOpts)]
+        lib.nmpc_get_opts.argtypes = [vp, C.POINTER(IpmOpts)]
+        lib.nmpc_iterate_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        lib.nmpc_reset.argtypes = [vp]
+        lib.nmpc_reset_async.argtypes = [vp, vp]
+        lib.nmpc_set_iterate_host.argtypes = [vp, C.c_int, dp, dp]
+        lib.nmpc_get_iterate_host.argtypes = [vp, C.c_int, dp, dp]
+        lib.nmpc_rti_solve_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp, dp, C.c_int, ip, ip, dp, vp]
+        lib.nmpc_rti_solve_host.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp, dp, ip, ip]
+        lib.nmpc_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+        lib.nmpc_last_launches.argtypes = [vp]
+        lib.nmpc_dims.argtypes = [C.c_int, C.POINTER(Dims)]
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nmpc_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")

@@ -36,34 +36,77 @@ struct IpmOpts {
     int iter_max, cond_pred_corr;
 };
 
-// per-stage record layout of one tile (offsets in units of LANES doubles)
+// Per-stage record layout of one tile.  Four field groups, each its own array
+// [stage][field][lane] so that every sweep can fetch exactly the contiguous field ranges it
+// needs with a few 1-D bulk copies (offsets in units of LANES doubles):
+//   LIN : QP data written by K1/K2, read-only for K3
+//   IT  : QP iterate (slacks, multipliers, primal, dynamics multipliers)
+//   ST  : steps
+//   FA  : factorisation of the last B sweep
 template <int NV_>
 struct Rec {
     static constexpr int NV = NV_, NX = 3 + 2 * NV, NU = NV, NZ = NX + NU, NC = 1 + 3 * NV, NB2 = 2 * NV;
-    // QP data, written by K1/K2
+    // ---- LIN
     static constexpr int E = 0;                 // 3*NC   pose rows of [A|B], columns [theta | actual | ref | u]
-    static constexpr int B0 = E + 3 * NC;       // NX     b = phi(x,u) - x_next
-    static constexpr int Q = B0 + NX;           // NZ     QP gradient, order [u; x]
-    static constexpr int DLB = Q + NZ;          // NB2    lb - z   for [u; ref]
+    static constexpr int DLB = E + 3 * NC;      // NB2    lb - z   for [u; ref]
     static constexpr int DUB = DLB + NB2;       // NB2    ub - z
-    // QP iterate
-    static constexpr int Z = DUB + NB2;         // NZ     [u; x]
+    static constexpr int Q = DUB + NB2;         // NZ     QP gradient, order [u; x]
+    static constexpr int B0 = Q + NZ;           // NX     b = phi(x,u) - x_next
+    static constexpr int NF_LIN = B0 + NX;
+    // ---- IT
+    static constexpr int T = 0;                 // 2*NB2  slacks, lower then upper
+    static constexpr int LAM = T + 2 * NB2;     // 2*NB2
+    static constexpr int Z = LAM + 2 * NB2;     // NZ     [u; x]
     static constexpr int PI = Z + NZ;           // NX     multiplier of the dynamics that define x_k
-    static constexpr int LAM = PI + NX;         // 2*NB2  lower then upper
-    static constexpr int T = LAM + 2 * NB2;     // 2*NB2
-    // steps
-    static constexpr int DZA = T + 2 * NB2;     // NZ     predictor (affine) step
-    static constexpr int DZ = DZA + NZ;         // NZ     final step
+    static constexpr int NF_IT = PI + NX;
+    // ---- ST
+    static constexpr int DZ = 0;                // NZ     final step
     static constexpr int MC = DZ + NZ;          // 2*NB2  dt_aff * dlam_aff
-    // factorisation
-    static constexpr int LUU = MC + 2 * NB2;    // NV(NV+1)/2 row-packed lower, diagonal stored inverted
+    static constexpr int DZA = MC + 2 * NB2;    // NZ     predictor (affine) step
+    static constexpr int NF_ST = DZA + NZ;
+    // ---- FA
+    static constexpr int LUU = 0;               // NV(NV+1)/2 row-packed lower, diagonal stored inverted
     static constexpr int KH = LUU + NV * (NV + 1) / 2;   // NV*NX  K = Luu^-1 S
-    static constexpr int LH = KH + NV * NX;     // NV     Luu^-1 q_u (predictor)
-    static constexpr int LHD = LH + NV;         // NV     Luu^-1 q_u (delta)
-    static constexpr int RB = LHD + NV;         // NX     dynamics residual
-    static constexpr int NF = RB + NX;
+    static constexpr int LHD = KH + NV * NX;    // NV     Luu^-1 q_u (delta)
+    static constexpr int LH = LHD + NV;         // NV     Luu^-1 q_u (predictor)
+    static constexpr int RB = LH + NV;          // NX     dynamics residual
+    static constexpr int NF_FA = RB + NX;
+
+    static constexpr int NF = NF_LIN + NF_IT + NF_ST + NF_FA;
+    // a tile = the four group arrays back to back
+    static constexpr size_t OFF_LIN = 0;
+    static constexpr size_t OFF_IT = OFF_LIN + (size_t)(NSTAGE + 1) * NF_LIN * LANES;
+    static constexpr size_t OFF_ST = OFF_IT + (size_t)(NSTAGE + 1) * NF_IT * LANES;
+    static constexpr size_t OFF_FA = OFF_ST + (size_t)(NSTAGE + 1) * NF_ST * LANES;
     static constexpr size_t tile_doubles = (size_t)(NSTAGE + 1) * NF * LANES;
 };
+
+// lane-resolved views of one stage: `in` pointers may point into a shared-memory copy (device
+// pipeline) or straight into the tile (host emulation / K1 / K4); field stride is LANES
+struct StageIn { const double *lin, *it, *st, *fa; };
+struct StageOut { double *it, *st, *fa; };
+
+template <int NV>
+NMPC_HD StageOut tile_stage_out(double* tile_lane, int k)
+{
+    using R = Rec<NV>;
+    StageOut o;
+    o.it = tile_lane + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
+    o.st = tile_lane + R::OFF_ST + (size_t)k * R::NF_ST * LANES;
+    o.fa = tile_lane + R::OFF_FA + (size_t)k * R::NF_FA * LANES;
+    return o;
+}
+template <int NV>
+NMPC_HD StageIn tile_stage_in(const double* tile_lane, int k)
+{
+    using R = Rec<NV>;
+    StageIn i;
+    i.lin = tile_lane + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES;
+    i.it = tile_lane + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
+    i.st = tile_lane + R::OFF_ST + (size_t)k * R::NF_ST * LANES;
+    i.fa = tile_lane + R::OFF_FA + (size_t)k * R::NF_FA * LANES;
+    return i;
+}
 
 // stage-wise problem tables shared by all instances (what the C-ABI setters fill)
 struct Tables {
@@ -179,7 +222,8 @@ struct Rti {
     }
 
     // ------------------------------------------------------------------------------------
-    // K1+K2 for one (instance, stage): writes the QP record of stage k.
+    // K1+K2 for one (instance, stage): writes the LIN record of stage k (and, for stage 0, the
+    // constant stage-0 state of the QP into IT.Z).
     //   xk, uk, xk1: iterate of this stage (uk, xk1 unused for k == N);  yref: nyref entries
     //   (3 = pose only, NY = full); We: terminal weight diagonal (broadcast or per instance).
     // K2 (ocp_nlp_cost_nls with y=[x;u], scripts/<m>/generate_c_code.py:30-39): gradient
@@ -187,7 +231,7 @@ struct Rti {
     // ------------------------------------------------------------------------------------
     NMPC_HD static void linearize_stage(int k, const double* xk, const double* uk, const double* xk1,
                                         const double* yref, int nyref, const double* x0bar,
-                                        const Tables& tb, const double* We, double* rec)
+                                        const Tables& tb, const double* We, double* lin, double* it)
     {
         if (k < NSTAGE) {
             double xn[NX], Ep[3][NC];
@@ -195,53 +239,53 @@ struct Rti {
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int c = 0; c < NC; c++) rec[(R::E + i * NC + c) * LANES] = Ep[i][c];
+                for (int c = 0; c < NC; c++) lin[(R::E + i * NC + c) * LANES] = Ep[i][c];
 #pragma unroll
-            for (int i = 0; i < NX; i++) rec[(R::B0 + i) * LANES] = xn[i] - xk1[i];
+            for (int i = 0; i < NX; i++) lin[(R::B0 + i) * LANES] = xn[i] - xk1[i];
             const double* Wk = tb.W + k * NY;
 #pragma unroll
             for (int c = 0; c < NU; c++) {
                 const double yr = (NX + c < nyref) ? yref[NX + c] : 0.0;
-                rec[(R::Q + c) * LANES] = (tb.dt * Wk[NX + c]) * (uk[c] - yr);
-                rec[(R::DLB + c) * LANES] = tb.lbu[k * NV + c] - uk[c];
-                rec[(R::DUB + c) * LANES] = tb.ubu[k * NV + c] - uk[c];
+                lin[(R::Q + c) * LANES] = (tb.dt * Wk[NX + c]) * (uk[c] - yr);
+                lin[(R::DLB + c) * LANES] = tb.lbu[k * NV + c] - uk[c];
+                lin[(R::DUB + c) * LANES] = tb.ubu[k * NV + c] - uk[c];
             }
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 const double yr = (j < nyref) ? yref[j] : 0.0;
-                rec[(R::Q + NU + j) * LANES] = (tb.dt * Wk[j]) * (xk[j] - yr);
+                lin[(R::Q + NU + j) * LANES] = (tb.dt * Wk[j]) * (xk[j] - yr);
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < NU; c++) rec[(R::Q + c) * LANES] = 0.0;
+            for (int c = 0; c < NU; c++) lin[(R::Q + c) * LANES] = 0.0;
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 const double yr = (j < nyref) ? yref[j] : 0.0;
-                rec[(R::Q + NU + j) * LANES] = We[j] * (xk[j] - yr);
+                lin[(R::Q + NU + j) * LANES] = We[j] * (xk[j] - yr);
             }
         }
         if (k >= 1) {
 #pragma unroll
             for (int c = 0; c < NV; c++) {
-                rec[(R::DLB + NV + c) * LANES] = tb.lbx[(k - 1) * NV + c] - xk[3 + NV + c];
-                rec[(R::DUB + NV + c) * LANES] = tb.ubx[(k - 1) * NV + c] - xk[3 + NV + c];
+                lin[(R::DLB + NV + c) * LANES] = tb.lbx[(k - 1) * NV + c] - xk[3 + NV + c];
+                lin[(R::DUB + NV + c) * LANES] = tb.ubx[(k - 1) * NV + c] - xk[3 + NV + c];
             }
         } else {
             // x0 elimination (d_ocp_qp_reduce_eq_dof): the stage-0 state is the constant x0bar - x_0
 #pragma unroll
-            for (int j = 0; j < NX; j++) rec[(R::Z + NU + j) * LANES] = x0bar[j] - xk[j];
+            for (int j = 0; j < NX; j++) it[(R::Z + NU + j) * LANES] = x0bar[j] - xk[j];
         }
     }
 
     // ------------------------------------------------------------------------------------
     // structured products with [B A] of one stage
     // ------------------------------------------------------------------------------------
-    NMPC_HD static void load_lin(const double* rec, const double* lti, L& l)
+    NMPC_HD static void load_lin(const double* lin, const double* lti, L& l)
     {
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int c = 0; c < NC; c++) l.E[i][c] = rec[(R::E + i * NC + c) * LANES];
+            for (int c = 0; c < NC; c++) l.E[i][c] = lin[(R::E + i * NC + c) * LANES];
 #pragma unroll
         for (int c = 0; c < NV; c++) { l.av[c] = lti[c]; l.ar[c] = lti[NV + c]; l.au[c] = lti[2 * NV + c]; l.ru[c] = lti[3 * NV + c]; }
     }
@@ -308,15 +352,15 @@ struct Rti {
     }
 
     // u = -Luu^-T (lh + K dx), Luu row-packed with inverted diagonal
-    NMPC_HD static void solve_u(const double* rec, int lh_field, bool with_K, const double* dx, double* du)
+    NMPC_HD static void solve_u(const double* fa, int lh_field, bool with_K, const double* dx, double* du)
     {
         double v[NV];
 #pragma unroll
         for (int a = 0; a < NV; a++) {
-            double s = rec[(lh_field + a) * LANES];
+            double s = fa[(lh_field + a) * LANES];
             if (with_K) {
 #pragma unroll
-                for (int j = 0; j < NX; j++) s += rec[(R::KH + a * NX + j) * LANES] * dx[j];
+                for (int j = 0; j < NX; j++) s += fa[(R::KH + a * NX + j) * LANES] * dx[j];
             }
             v[a] = -s;
         }
@@ -324,8 +368,8 @@ struct Rti {
         for (int a = NV - 1; a >= 0; a--) {
             double s = v[a];
 #pragma unroll
-            for (int b = a + 1; b < NV; b++) s -= rec[(R::LUU + b * (b + 1) / 2 + a) * LANES] * du[b];
-            du[a] = s * rec[(R::LUU + a * (a + 1) / 2 + a) * LANES];
+            for (int b = a + 1; b < NV; b++) s -= fa[(R::LUU + b * (b + 1) / 2 + a) * LANES] * du[b];
+            du[a] = s * fa[(R::LUU + a * (a + 1) / 2 + a) * LANES];
         }
     }
 
@@ -338,426 +382,443 @@ struct Rti {
         int cond_fallbacks;
     };
 
-    // ------------------------------------------------------------------------------------
-    // B sweep: (apply previous step) + residuals + Riccati factorisation, stage N..0
-    // ------------------------------------------------------------------------------------
-    NMPC_HD static void sweep_B(double* base, const Tables& tb, const double* We, const IpmOpts& o, bool first,
-                                double a_step, double sigmu, double mcw, double* nrm, double* mu_out, double* lru_out)
-    {
+    // ====================================================================================
+    // K3 sweeps, written as per-stage functions with explicit carries so that the device
+    // pipeline can stream one stage record at a time through shared memory.
+    // ====================================================================================
+
+    // ---- B sweep: (apply previous step) + residuals + Riccati factorisation, stage N..0 -----
+    struct CarryB {
         double P[NPK], pv[NX], pi_o[NX], dpi[NX], xn[NX];
-        double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, musum = 0.0, lru = 0.0;
+        double ng, nb, nd, nm, musum, lru;
+        NMPC_HD void init()
+        {
 #pragma unroll
-        for (int i = 0; i < NX; i++) { pv[i] = 0.0; pi_o[i] = 0.0; dpi[i] = 0.0; xn[i] = 0.0; }
+            for (int i = 0; i < NX; i++) { pv[i] = 0.0; pi_o[i] = 0.0; dpi[i] = 0.0; xn[i] = 0.0; }
 #pragma unroll
-        for (int i = 0; i < NPK; i++) P[i] = 0.0;
+            for (int i = 0; i < NPK; i++) P[i] = 0.0;
+            ng = nb = nd = nm = musum = lru = 0.0;
+        }
+    };
+    // reads : LIN[all], IT[all], ST[DZ, MC] (not when first)      writes: IT[all], FA[LUU,KH,LH,RB]
+    NMPC_HD static void stage_B(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+                                const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy)
+    {
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+        L lin;
+        if (hasU) load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+        double Hu[NV], Hx[NX], qu[NV], qx[NX];
+#pragma unroll
+        for (int c = 0; c < NV; c++) { Hu[c] = hasU ? tb.dt * tb.W[k * NY + NX + c] : 0.0; qu[c] = in.lin[(R::Q + c) * LANES]; }
+#pragma unroll
+        for (int j = 0; j < NX; j++) { Hx[j] = hasU ? tb.dt * tb.W[k * NY + j] : We[j]; qx[j] = in.lin[(R::Q + NU + j) * LANES]; }
 
-        for (int k = NSTAGE; k >= 0; k--) {
-            double* rec = base + (size_t)k * R::NF * LANES;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
-            L lin;
-            if (hasU) load_lin(rec, tb.lti + k * 4 * NV, lin);
-            double Hu[NV], Hx[NX], qu[NV], qx[NX];
+        double zu[NV], zx[NX], pin[NX];
+        double ll[NB2], lu[NB2], tl[NB2], tu[NB2], dl[NB2], du_[NB2];
 #pragma unroll
-            for (int c = 0; c < NV; c++) { Hu[c] = hasU ? tb.dt * tb.W[k * NY + NX + c] : 0.0; qu[c] = rec[(R::Q + c) * LANES]; }
-#pragma unroll
-            for (int j = 0; j < NX; j++) { Hx[j] = hasU ? tb.dt * tb.W[k * NY + j] : We[j]; qx[j] = rec[(R::Q + NU + j) * LANES]; }
+        for (int b = 0; b < NB2; b++) { dl[b] = in.lin[(R::DLB + b) * LANES]; du_[b] = in.lin[(R::DUB + b) * LANES]; }
 
-            double zu[NV], zx[NX], pin[NX];
-            double ll[NB2], lu[NB2], tl[NB2], tu[NB2], dl[NB2], du_[NB2];
+        double v1u[NV], v1x[NX], v2u[NV], v2x[NX];
+        if (hasU) { apply_T(lin, cy.pi_o, v1u, v1x); apply_T(lin, cy.dpi, v2u, v2x); }
+        else {
 #pragma unroll
-            for (int b = 0; b < NB2; b++) { dl[b] = rec[(R::DLB + b) * LANES]; du_[b] = rec[(R::DUB + b) * LANES]; }
+            for (int c = 0; c < NV; c++) { v1u[c] = 0.0; v2u[c] = 0.0; }
+#pragma unroll
+            for (int j = 0; j < NX; j++) { v1x[j] = 0.0; v2x[j] = 0.0; }
+        }
+        double pi_old[NX];
 
-            double v1u[NV], v1x[NX], v2u[NV], v2x[NX];
-            if (hasU) { apply_T(lin, pi_o, v1u, v1x); apply_T(lin, dpi, v2u, v2x); }
-            else {
+        if (first) {
+            // cold start (HPIPM INIT_VAR with warm_start = 0): z = 0, pi = 0, slacks from the
+            // bounds with the thr0 projection, lam = mu0 / t
 #pragma unroll
-                for (int c = 0; c < NV; c++) { v1u[c] = 0.0; v2u[c] = 0.0; }
+            for (int c = 0; c < NV; c++) zu[c] = 0.0;
 #pragma unroll
-                for (int j = 0; j < NX; j++) { v1x[j] = 0.0; v2x[j] = 0.0; }
+            for (int j = 0; j < NX; j++) { zx[j] = hasX ? 0.0 : in.it[(R::Z + NU + j) * LANES]; pin[j] = 0.0; pi_old[j] = 0.0; }
+#pragma unroll
+            for (int b = 0; b < NB2; b++) {
+                const bool act = (b < NV) ? hasU : hasX;
+                double zb = 0.0, t_l = -dl[b], t_u = du_[b];
+                if (t_l < o.thr0) {
+                    if (t_u < o.thr0) { zb = 0.5 * (dl[b] + du_[b]); t_l = o.thr0; t_u = o.thr0; }
+                    else { t_l = o.thr0; zb = dl[b] + o.thr0; }
+                } else if (t_u < o.thr0) { t_u = o.thr0; zb = du_[b] - o.thr0; }
+                if (act) {
+                    if (b < NV) zu[b] = zb; else zx[3 + b] = zb;      // ref state index 3+NV+(b-NV)
+                    tl[b] = t_l; tu[b] = t_u; ll[b] = o.mu0 / t_l; lu[b] = o.mu0 / t_u;
+                } else { tl[b] = 1.0; tu[b] = 1.0; ll[b] = 0.0; lu[b] = 0.0; }
             }
-            double pi_old[NX];
-
-            if (first) {
-                // cold start (HPIPM INIT_VAR with warm_start = 0): z = 0, pi = 0, slacks from the
-                // bounds with the thr0 projection, lam = mu0 / t
+        } else {
+            double dzu[NV], dzx[NX];
 #pragma unroll
-                for (int c = 0; c < NV; c++) zu[c] = 0.0;
-#pragma unroll
-                for (int j = 0; j < NX; j++) { zx[j] = hasX ? 0.0 : rec[(R::Z + NU + j) * LANES]; pin[j] = 0.0; pi_old[j] = 0.0; }
-#pragma unroll
-                for (int b = 0; b < NB2; b++) {
-                    const bool act = (b < NV) ? hasU : hasX;
-                    double zb = 0.0, t_l = -dl[b], t_u = du_[b];
-                    if (t_l < o.thr0) {
-                        if (t_u < o.thr0) { zb = 0.5 * (dl[b] + du_[b]); t_l = o.thr0; t_u = o.thr0; }
-                        else { t_l = o.thr0; zb = dl[b] + o.thr0; }
-                    } else if (t_u < o.thr0) { t_u = o.thr0; zb = du_[b] - o.thr0; }
-                    if (act) {
-                        if (b < NV) zu[b] = zb; else zx[3 + b] = zb;      // ref state index 3+NV+(b-NV)
-                        tl[b] = t_l; tu[b] = t_u; ll[b] = o.mu0 / t_l; lu[b] = o.mu0 / t_u;
-                    } else { tl[b] = 1.0; tu[b] = 1.0; ll[b] = 0.0; lu[b] = 0.0; }
-                }
-            } else {
-                double dzu[NV], dzx[NX];
-#pragma unroll
-                for (int c = 0; c < NV; c++) { zu[c] = rec[(R::Z + c) * LANES]; dzu[c] = hasU ? rec[(R::DZ + c) * LANES] : 0.0; }
-#pragma unroll
-                for (int j = 0; j < NX; j++) {
-                    zx[j] = rec[(R::Z + NU + j) * LANES];
-                    dzx[j] = hasX ? rec[(R::DZ + NU + j) * LANES] : 0.0;
-                    pin[j] = hasX ? rec[(R::PI + j) * LANES] : 0.0;
-                    pi_old[j] = pin[j];
-                }
-                double ldo[NB2], dld[NB2];   // (lam_u - lam_l) old, (dlam_l - dlam_u)
-#pragma unroll
-                for (int b = 0; b < NB2; b++) {
-                    const bool act = (b < NV) ? hasU : hasX;
-                    if (act) {
-                        ll[b] = rec[(R::LAM + b) * LANES]; lu[b] = rec[(R::LAM + NB2 + b) * LANES];
-                        tl[b] = rec[(R::T + b) * LANES];   tu[b] = rec[(R::T + NB2 + b) * LANES];
-                        const double mc_l = rec[(R::MC + b) * LANES], mc_u = rec[(R::MC + NB2 + b) * LANES];
-                        const double zb = (b < NV) ? zu[b] : zx[3 + b];
-                        const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
-                        const double rd_l = dl[b] - zb + tl[b], rd_u = -du_[b] + zb + tu[b];
-                        const double rm_l = ll[b] * tl[b] - o.tau_min + mcw * mc_l - sigmu;
-                        const double rm_u = lu[b] * tu[b] - o.tau_min + mcw * mc_u - sigmu;
-                        const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
-                        const double dl_l = -(ll[b] * dt_l + rm_l) / tl[b];
-                        const double dl_u = -(lu[b] * dt_u + rm_u) / tu[b];
-                        ldo[b] = lu[b] - ll[b];
-                        dld[b] = dl_l - dl_u;
-                        ll[b] += a_step * dl_l; lu[b] += a_step * dl_u;
-                        tl[b] += a_step * dt_l; tu[b] += a_step * dt_u;
-                    } else { ll[b] = 0.0; lu[b] = 0.0; tl[b] = 1.0; tu[b] = 1.0; ldo[b] = 0.0; dld[b] = 0.0; }
-                }
-                // stationarity residual of the Newton system, control rows (diagnostic: the
-                // quantity HPIPM's iterative refinement would test)
-                if (hasU) {
-#pragma unroll
-                    for (int c = 0; c < NV; c++) {
-                        const double r = qu[c] + Hu[c] * zu[c] + ldo[c] + v1u[c] + Hu[c] * dzu[c] - dld[c] + v2u[c];
-                        lru = fmax(lru, fabs(r));
-                    }
-                }
-                // adjoint recursion for the multiplier step of the dynamics that define x_k
-                if (hasX) {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) {
-                        double r = qx[j] + Hx[j] * zx[j] - pin[j] + v1x[j] + Hx[j] * dzx[j] + v2x[j];
-                        if (j >= 3 + NV) r += ldo[j - 3] - dld[j - 3];
-                        dpi[j] = r;
-                        pin[j] += a_step * r;
-                        zx[j] += a_step * dzx[j];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < NV; c++) zu[c] += a_step * dzu[c];
-            }
-
-            // ---- residuals at the (new) iterate -------------------------------------------
-            double rgu[NV], rgx[NX], rb[NX];
-#pragma unroll
-            for (int c = 0; c < NV; c++) {
-                rgu[c] = qu[c] + Hu[c] * zu[c] + (lu[c] - ll[c]) + (v1u[c] + a_step * v2u[c]);
-                if (hasU) ng = fmax(ng, fabs(rgu[c]));
-            }
+            for (int c = 0; c < NV; c++) { zu[c] = in.it[(R::Z + c) * LANES]; dzu[c] = hasU ? in.st[(R::DZ + c) * LANES] : 0.0; }
 #pragma unroll
             for (int j = 0; j < NX; j++) {
-                double r = qx[j] + Hx[j] * zx[j] - pin[j] + (v1x[j] + a_step * v2x[j]);
-                if (j >= 3 + NV) r += lu[j - 3] - ll[j - 3];
-                rgx[j] = r;
-                if (hasX) ng = fmax(ng, fabs(r));
+                zx[j] = in.it[(R::Z + NU + j) * LANES];
+                dzx[j] = hasX ? in.st[(R::DZ + NU + j) * LANES] : 0.0;
+                pin[j] = hasX ? in.it[(R::PI + j) * LANES] : 0.0;
+                pi_old[j] = pin[j];
             }
-            if (hasU) {
-                apply(lin, zu, zx, rb);
-#pragma unroll
-                for (int i = 0; i < NX; i++) { rb[i] += rec[(R::B0 + i) * LANES] - xn[i]; nb = fmax(nb, fabs(rb[i])); }
-            }
-            double Gam[NB2], gam[NB2];
+            double ldo[NB2], dld[NB2];   // (lam_u - lam_l) old, (dlam_l - dlam_u)
 #pragma unroll
             for (int b = 0; b < NB2; b++) {
                 const bool act = (b < NV) ? hasU : hasX;
                 if (act) {
+                    ll[b] = in.it[(R::LAM + b) * LANES]; lu[b] = in.it[(R::LAM + NB2 + b) * LANES];
+                    tl[b] = in.it[(R::T + b) * LANES];   tu[b] = in.it[(R::T + NB2 + b) * LANES];
+                    const double mc_l = in.st[(R::MC + b) * LANES], mc_u = in.st[(R::MC + NB2 + b) * LANES];
                     const double zb = (b < NV) ? zu[b] : zx[3 + b];
+                    const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
                     const double rd_l = dl[b] - zb + tl[b], rd_u = -du_[b] + zb + tu[b];
-                    const double pm_l = ll[b] * tl[b], pm_u = lu[b] * tu[b];
-                    musum += pm_l + pm_u;
-                    const double rm_l = pm_l - o.tau_min, rm_u = pm_u - o.tau_min;
-                    nd = fmax(nd, fmax(fabs(rd_l), fabs(rd_u)));
-                    nm = fmax(nm, fmax(fabs(rm_l), fabs(rm_u)));
-                    const double ti_l = tl[b] < o.t_min ? 1.0 / o.t_min : 1.0 / tl[b];
-                    const double ti_u = tu[b] < o.t_min ? 1.0 / o.t_min : 1.0 / tu[b];
-                    const double l_l = ll[b] < o.lam_min ? o.lam_min : ll[b];
-                    const double l_u = lu[b] < o.lam_min ? o.lam_min : lu[b];
-                    Gam[b] = ti_l * l_l + ti_u * l_u;
-                    gam[b] = ti_l * (rm_l - ll[b] * rd_l) - ti_u * (rm_u - lu[b] * rd_u);
-                } else { Gam[b] = 0.0; gam[b] = 0.0; }
+                    const double rm_l = ll[b] * tl[b] - o.tau_min + mcw * mc_l - sigmu;
+                    const double rm_u = lu[b] * tu[b] - o.tau_min + mcw * mc_u - sigmu;
+                    const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
+                    const double dl_l = -(ll[b] * dt_l + rm_l) / tl[b];
+                    const double dl_u = -(lu[b] * dt_u + rm_u) / tu[b];
+                    ldo[b] = lu[b] - ll[b];
+                    dld[b] = dl_l - dl_u;
+                    ll[b] += a_step * dl_l; lu[b] += a_step * dl_u;
+                    tl[b] += a_step * dt_l; tu[b] += a_step * dt_u;
+                } else { ll[b] = 0.0; lu[b] = 0.0; tl[b] = 1.0; tu[b] = 1.0; ldo[b] = 0.0; dld[b] = 0.0; }
             }
-
-            // ---- store the iterate ----------------------------------------------------------
+            // stationarity residual of the Newton system, control rows (diagnostic: the quantity
+            // HPIPM's iterative refinement would test)
+            if (hasU) {
 #pragma unroll
-            for (int c = 0; c < NV; c++) rec[(R::Z + c) * LANES] = zu[c];
+                for (int c = 0; c < NV; c++) {
+                    const double r = qu[c] + Hu[c] * zu[c] + ldo[c] + v1u[c] + Hu[c] * dzu[c] - dld[c] + v2u[c];
+                    cy.lru = fmax(cy.lru, fabs(r));
+                }
+            }
+            // adjoint recursion for the multiplier step of the dynamics that define x_k
             if (hasX) {
 #pragma unroll
-                for (int j = 0; j < NX; j++) { rec[(R::Z + NU + j) * LANES] = zx[j]; rec[(R::PI + j) * LANES] = pin[j]; }
+                for (int j = 0; j < NX; j++) {
+                    double r = qx[j] + Hx[j] * zx[j] - pin[j] + v1x[j] + Hx[j] * dzx[j] + v2x[j];
+                    if (j >= 3 + NV) r += ldo[j - 3] - dld[j - 3];
+                    cy.dpi[j] = r;
+                    pin[j] += a_step * r;
+                    zx[j] += a_step * dzx[j];
+                }
             }
 #pragma unroll
-            for (int b = 0; b < NB2; b++) {
-                rec[(R::LAM + b) * LANES] = ll[b]; rec[(R::LAM + NB2 + b) * LANES] = lu[b];
-                rec[(R::T + b) * LANES] = tl[b];   rec[(R::T + NB2 + b) * LANES] = tu[b];
-            }
+            for (int c = 0; c < NV; c++) zu[c] += a_step * dzu[c];
+        }
 
-            // ---- Riccati step ---------------------------------------------------------------
-            // gradient of the stage incl. barrier terms and the cost-to-go of the successor
-            double gu[NV], gx[NX];
+        // ---- residuals at the (new) iterate -----------------------------------------------
+        double rgu[NV], rgx[NX], rb[NX];
 #pragma unroll
-            for (int c = 0; c < NV; c++) gu[c] = rgu[c] + gam[c];
+        for (int c = 0; c < NV; c++) {
+            rgu[c] = qu[c] + Hu[c] * zu[c] + (lu[c] - ll[c]) + (v1u[c] + a_step * v2u[c]);
+            if (hasU) cy.ng = fmax(cy.ng, fabs(rgu[c]));
+        }
 #pragma unroll
-            for (int j = 0; j < NX; j++) gx[j] = rgx[j] + (j >= 3 + NV ? gam[j - 3] : 0.0);
-            if (hasU) {
+        for (int j = 0; j < NX; j++) {
+            double r = qx[j] + Hx[j] * zx[j] - pin[j] + (v1x[j] + a_step * v2x[j]);
+            if (j >= 3 + NV) r += lu[j - 3] - ll[j - 3];
+            rgx[j] = r;
+            if (hasX) cy.ng = fmax(cy.ng, fabs(r));
+        }
+        if (hasU) {
+            apply(lin, zu, zx, rb);
 #pragma unroll
-                for (int i = 0; i < NX; i++) rec[(R::RB + i) * LANES] = rb[i];
-                double Pb[NX];
+            for (int i = 0; i < NX; i++) { rb[i] += in.lin[(R::B0 + i) * LANES] - cy.xn[i]; cy.nb = fmax(cy.nb, fabs(rb[i])); }
+        }
+        double Gam[NB2], gam[NB2];
+#pragma unroll
+        for (int b = 0; b < NB2; b++) {
+            const bool act = (b < NV) ? hasU : hasX;
+            if (act) {
+                const double zb = (b < NV) ? zu[b] : zx[3 + b];
+                const double rd_l = dl[b] - zb + tl[b], rd_u = -du_[b] + zb + tu[b];
+                const double pm_l = ll[b] * tl[b], pm_u = lu[b] * tu[b];
+                cy.musum += pm_l + pm_u;
+                const double rm_l = pm_l - o.tau_min, rm_u = pm_u - o.tau_min;
+                cy.nd = fmax(cy.nd, fmax(fabs(rd_l), fabs(rd_u)));
+                cy.nm = fmax(cy.nm, fmax(fabs(rm_l), fabs(rm_u)));
+                const double ti_l = tl[b] < o.t_min ? 1.0 / o.t_min : 1.0 / tl[b];
+                const double ti_u = tu[b] < o.t_min ? 1.0 / o.t_min : 1.0 / tu[b];
+                const double l_l = ll[b] < o.lam_min ? o.lam_min : ll[b];
+                const double l_u = lu[b] < o.lam_min ? o.lam_min : lu[b];
+                Gam[b] = ti_l * l_l + ti_u * l_u;
+                gam[b] = ti_l * (rm_l - ll[b] * rd_l) - ti_u * (rm_u - lu[b] * rd_u);
+            } else { Gam[b] = 0.0; gam[b] = 0.0; }
+        }
+
+        // ---- store the iterate --------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < NV; c++) out.it[(R::Z + c) * LANES] = zu[c];
+        if (hasX) {
+#pragma unroll
+            for (int j = 0; j < NX; j++) { out.it[(R::Z + NU + j) * LANES] = zx[j]; out.it[(R::PI + j) * LANES] = pin[j]; }
+        }
+#pragma unroll
+        for (int b = 0; b < NB2; b++) {
+            out.it[(R::LAM + b) * LANES] = ll[b]; out.it[(R::LAM + NB2 + b) * LANES] = lu[b];
+            out.it[(R::T + b) * LANES] = tl[b];   out.it[(R::T + NB2 + b) * LANES] = tu[b];
+        }
+
+        // ---- Riccati step -------------------------------------------------------------------
+        // gradient of the stage incl. barrier terms and the cost-to-go of the successor
+        double gu[NV], gx[NX];
+#pragma unroll
+        for (int c = 0; c < NV; c++) gu[c] = rgu[c] + gam[c];
+#pragma unroll
+        for (int j = 0; j < NX; j++) gx[j] = rgx[j] + (j >= 3 + NV ? gam[j - 3] : 0.0);
+        if (hasU) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) out.fa[(R::RB + i) * LANES] = rb[i];
+            double Pb[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                double s = cy.pv[i];
+#pragma unroll
+                for (int j = 0; j < NX; j++) s += cy.P[pk(i, j)] * rb[j];
+                Pb[i] = s;
+            }
+            double tu_[NV], tx_[NX];
+            apply_T(lin, Pb, tu_, tx_);
+#pragma unroll
+            for (int c = 0; c < NV; c++) gu[c] += tu_[c];
+#pragma unroll
+            for (int j = 0; j < NX; j++) gx[j] += tx_[j];
+
+            // M = [B A]' P [B A] + diag(H + Gamma + reg), packed lower in z order
+            constexpr int NMK = NZ * (NZ + 1) / 2;
+            double Mk[NMK];
+#pragma unroll
+            for (int j = 0; j < NZ; j++) {
+                if (!hasX && j >= NV) break;
+                double g[NX], cu[NV], cx[NX];
+                P_col(cy.P, lin, j, g);
+                apply_T(lin, g, cu, cx);
+#pragma unroll
+                for (int i = j; i < NZ; i++) Mk[i * (i + 1) / 2 + j] = (i < NV) ? cu[i] : cx[i - NV];
+            }
+#pragma unroll
+            for (int c = 0; c < NV; c++) Mk[c * (c + 1) / 2 + c] += Hu[c] + o.reg_prim + Gam[c];
+            // Cholesky of the control block, diagonal kept inverted
+            double Luu[NLU];
+#pragma unroll
+            for (int a = 0; a < NV; a++) {
+                double d = Mk[a * (a + 1) / 2 + a];
+#pragma unroll
+                for (int c = 0; c < a; c++) d -= Luu[a * (a + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
+                const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                Luu[a * (a + 1) / 2 + a] = inv;
+#pragma unroll
+                for (int b = a + 1; b < NV; b++) {
+                    double s = Mk[b * (b + 1) / 2 + a];
+#pragma unroll
+                    for (int c = 0; c < a; c++) s -= Luu[b * (b + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
+                    Luu[b * (b + 1) / 2 + a] = s * inv;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NLU; i++) out.fa[(R::LUU + i) * LANES] = Luu[i];
+            double lh[NV];
+#pragma unroll
+            for (int a = 0; a < NV; a++) {
+                double s = gu[a];
+#pragma unroll
+                for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * lh[c];
+                lh[a] = s * Luu[a * (a + 1) / 2 + a];
+                out.fa[(R::LH + a) * LANES] = lh[a];
+            }
+            if (hasX) {
+                double Kh[NV][NX];
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+#pragma unroll
+                    for (int a = 0; a < NV; a++) {
+                        double s = Mk[(NV + j) * (NV + j + 1) / 2 + a];
+#pragma unroll
+                        for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * Kh[c][j];
+                        Kh[a][j] = s * Luu[a * (a + 1) / 2 + a];
+                        out.fa[(R::KH + a * NX + j) * LANES] = Kh[a][j];
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < NX; i++) {
-                    double s = pv[i];
 #pragma unroll
-                    for (int j = 0; j < NX; j++) s += P[pk(i, j)] * rb[j];
-                    Pb[i] = s;
-                }
-                double tu_[NV], tx_[NX];
-                apply_T(lin, Pb, tu_, tx_);
+                    for (int j = 0; j <= i; j++) {
+                        double s = Mk[(NV + i) * (NV + i + 1) / 2 + NV + j];
 #pragma unroll
-                for (int c = 0; c < NV; c++) gu[c] += tu_[c];
-#pragma unroll
-                for (int j = 0; j < NX; j++) gx[j] += tx_[j];
-
-                // M = [B A]' P [B A] + diag(H + Gamma + reg), packed lower in z order
-                constexpr int NMK = NZ * (NZ + 1) / 2;
-                double Mk[NMK];
-#pragma unroll
-                for (int j = 0; j < NZ; j++) {
-                    if (!hasX && j >= NV) break;
-                    double g[NX], cu[NV], cx[NX];
-                    P_col(P, lin, j, g);
-                    apply_T(lin, g, cu, cx);
-#pragma unroll
-                    for (int i = j; i < NZ; i++) Mk[i * (i + 1) / 2 + j] = (i < NV) ? cu[i] : cx[i - NV];
-                }
-#pragma unroll
-                for (int c = 0; c < NV; c++) Mk[c * (c + 1) / 2 + c] += Hu[c] + o.reg_prim + Gam[c];
-                // Cholesky of the control block, diagonal kept inverted
-                double Luu[NLU];
-#pragma unroll
-                for (int a = 0; a < NV; a++) {
-                    double d = Mk[a * (a + 1) / 2 + a];
-#pragma unroll
-                    for (int c = 0; c < a; c++) d -= Luu[a * (a + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
-                    const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
-                    Luu[a * (a + 1) / 2 + a] = inv;
-#pragma unroll
-                    for (int b = a + 1; b < NV; b++) {
-                        double s = Mk[b * (b + 1) / 2 + a];
-#pragma unroll
-                        for (int c = 0; c < a; c++) s -= Luu[b * (b + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
-                        Luu[b * (b + 1) / 2 + a] = s * inv;
+                        for (int a = 0; a < NV; a++) s -= Kh[a][i] * Kh[a][j];
+                        if (i == j) s += Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0);
+                        cy.P[pk(i, j)] = s;
                     }
-                }
+                    double s = gx[i];
 #pragma unroll
-                for (int i = 0; i < NLU; i++) rec[(R::LUU + i) * LANES] = Luu[i];
-                double lh[NV];
-#pragma unroll
-                for (int a = 0; a < NV; a++) {
-                    double s = gu[a];
-#pragma unroll
-                    for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * lh[c];
-                    lh[a] = s * Luu[a * (a + 1) / 2 + a];
-                    rec[(R::LH + a) * LANES] = lh[a];
-                }
-                if (hasX) {
-                    double Kh[NV][NX];
-#pragma unroll
-                    for (int j = 0; j < NX; j++) {
-#pragma unroll
-                        for (int a = 0; a < NV; a++) {
-                            double s = Mk[(NV + j) * (NV + j + 1) / 2 + a];
-#pragma unroll
-                            for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * Kh[c][j];
-                            Kh[a][j] = s * Luu[a * (a + 1) / 2 + a];
-                            rec[(R::KH + a * NX + j) * LANES] = Kh[a][j];
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NX; i++) {
-#pragma unroll
-                        for (int j = 0; j <= i; j++) {
-                            double s = Mk[(NV + i) * (NV + i + 1) / 2 + NV + j];
-#pragma unroll
-                            for (int a = 0; a < NV; a++) s -= Kh[a][i] * Kh[a][j];
-                            if (i == j) s += Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0);
-                            P[pk(i, j)] = s;
-                        }
-                        double s = gx[i];
-#pragma unroll
-                        for (int a = 0; a < NV; a++) s -= Kh[a][i] * lh[a];
-                        pv[i] = s;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NX; i++) {
-#pragma unroll
-                    for (int j = 0; j <= i; j++) P[pk(i, j)] = (i == j) ? Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0) : 0.0;
-                    pv[i] = gx[i];
+                    for (int a = 0; a < NV; a++) s -= Kh[a][i] * lh[a];
+                    cy.pv[i] = s;
                 }
             }
-            // carries for stage k-1
+        } else {
 #pragma unroll
-            for (int j = 0; j < NX; j++) { pi_o[j] = pi_old[j]; xn[j] = zx[j]; }
-            if (first) {
+            for (int i = 0; i < NX; i++) {
 #pragma unroll
-                for (int j = 0; j < NX; j++) dpi[j] = 0.0;
+                for (int j = 0; j <= i; j++) cy.P[pk(i, j)] = (i == j) ? Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0) : 0.0;
+                cy.pv[i] = gx[i];
             }
         }
-        nrm[0] = ng; nrm[1] = nb; nrm[2] = nd; nrm[3] = nm;
-        *mu_out = musum / (double)NCON;
-        *lru_out = lru;
+        // carries for stage k-1
+#pragma unroll
+        for (int j = 0; j < NX; j++) { cy.pi_o[j] = pi_old[j]; cy.xn[j] = zx[j]; }
+        if (first) {
+#pragma unroll
+            for (int j = 0; j < NX; j++) cy.dpi[j] = 0.0;
+        }
     }
 
-    // ------------------------------------------------------------------------------------
-    // forward sweeps. delta == false: predictor (writes DZA, MC); delta == true: adds the delta
-    // step to the predictor (writes DZ).  Returns the ratio-test step and the three sums that
-    // give mu(alpha) = (S0 + alpha S1 + alpha^2 S2) / nc.
-    // ------------------------------------------------------------------------------------
-    NMPC_HD static void sweep_F(double* base, const Tables& tb, const IpmOpts& o, bool delta, double sigmu, double mcw,
-                                double* alpha_out, double* S)
+    // ---- forward sweeps.  delta == false: predictor (writes ST.DZA, ST.MC); delta == true: adds
+    // the delta step to the predictor (writes ST.DZ).  Accumulates the ratio-test step (negated,
+    // as HPIPM keeps it) and the three sums of mu(alpha) = (S0 + alpha S1 + alpha^2 S2) / nc.
+    struct CarryF {
+        double dx[NX], alpha, S0, S1, S2;
+        NMPC_HD void init()
+        {
+#pragma unroll
+            for (int j = 0; j < NX; j++) dx[j] = 0.0;
+            alpha = -1.0; S0 = S1 = S2 = 0.0;
+        }
+    };
+    // predictor reads: FA[all], LIN[E,DLB,DUB], IT[T,LAM,Z]            writes ST[MC,DZA]
+    // delta     reads: FA[LUU,KH,LHD], LIN[E,DLB,DUB], IT[T,LAM,Z], ST[MC,DZA]   writes ST[DZ]
+    NMPC_HD static void stage_F(int k, const StageIn& in, const StageOut& out, const Tables& tb, const IpmOpts& o,
+                                bool delta, double sigmu, double mcw, CarryF& cy)
     {
-        double dx[NX];
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+        double du[NV];
 #pragma unroll
-        for (int j = 0; j < NX; j++) dx[j] = 0.0;
-        double alpha = -1.0, S0 = 0.0, S1 = 0.0, S2 = 0.0;
-        for (int k = 0; k <= NSTAGE; k++) {
-            double* rec = base + (size_t)k * R::NF * LANES;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
-            double du[NV];
+        for (int c = 0; c < NV; c++) du[c] = 0.0;
+        if (hasU) solve_u(in.fa, delta ? R::LHD : R::LH, hasX, cy.dx, du);
+        double dzu[NV], dzx[NX];
+        if (!delta) {
 #pragma unroll
-            for (int c = 0; c < NV; c++) du[c] = 0.0;
-            if (hasU) solve_u(rec, delta ? R::LHD : R::LH, hasX, dx, du);
-            double dzu[NV], dzx[NX];
-            if (!delta) {
+            for (int c = 0; c < NV; c++) { dzu[c] = du[c]; out.st[(R::DZA + c) * LANES] = du[c]; }
 #pragma unroll
-                for (int c = 0; c < NV; c++) { dzu[c] = du[c]; rec[(R::DZA + c) * LANES] = du[c]; }
+            for (int j = 0; j < NX; j++) { dzx[j] = cy.dx[j]; out.st[(R::DZA + NU + j) * LANES] = cy.dx[j]; }
+        } else {
 #pragma unroll
-                for (int j = 0; j < NX; j++) { dzx[j] = dx[j]; rec[(R::DZA + NU + j) * LANES] = dx[j]; }
-            } else {
+            for (int c = 0; c < NV; c++) { dzu[c] = in.st[(R::DZA + c) * LANES] + du[c]; out.st[(R::DZ + c) * LANES] = dzu[c]; }
 #pragma unroll
-                for (int c = 0; c < NV; c++) { dzu[c] = rec[(R::DZA + c) * LANES] + du[c]; rec[(R::DZ + c) * LANES] = dzu[c]; }
+            for (int j = 0; j < NX; j++) { dzx[j] = in.st[(R::DZA + NU + j) * LANES] + cy.dx[j]; out.st[(R::DZ + NU + j) * LANES] = dzx[j]; }
+        }
 #pragma unroll
-                for (int j = 0; j < NX; j++) { dzx[j] = rec[(R::DZA + NU + j) * LANES] + dx[j]; rec[(R::DZ + NU + j) * LANES] = dzx[j]; }
-            }
-#pragma unroll
-            for (int b = 0; b < NB2; b++) {
-                const bool act = (b < NV) ? hasU : hasX;
-                if (act) {
-                    const double ll = rec[(R::LAM + b) * LANES], lu = rec[(R::LAM + NB2 + b) * LANES];
-                    const double tl = rec[(R::T + b) * LANES], tu = rec[(R::T + NB2 + b) * LANES];
-                    const double zb = (b < NV) ? rec[(R::Z + b) * LANES] : rec[(R::Z + NU + 3 + b) * LANES];
-                    const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
-                    const double rd_l = rec[(R::DLB + b) * LANES] - zb + tl, rd_u = -rec[(R::DUB + b) * LANES] + zb + tu;
-                    double rm_l = ll * tl - o.tau_min, rm_u = lu * tu - o.tau_min;
-                    if (delta) {
-                        rm_l += mcw * rec[(R::MC + b) * LANES] - sigmu;
-                        rm_u += mcw * rec[(R::MC + NB2 + b) * LANES] - sigmu;
-                    }
-                    const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
-                    const double dl_l = -(ll * dt_l + rm_l) / tl, dl_u = -(lu * dt_u + rm_u) / tu;
-                    if (!delta) { rec[(R::MC + b) * LANES] = dt_l * dl_l; rec[(R::MC + NB2 + b) * LANES] = dt_u * dl_u; }
-                    if (alpha * dl_l > ll) alpha = ll / dl_l;
-                    if (alpha * dt_l > tl) alpha = tl / dt_l;
-                    if (alpha * dl_u > lu) alpha = lu / dl_u;
-                    if (alpha * dt_u > tu) alpha = tu / dt_u;
-                    S0 += ll * tl + lu * tu;
-                    S1 += ll * dt_l + tl * dl_l + lu * dt_u + tu * dl_u;
-                    S2 += dl_l * dt_l + dl_u * dt_u;
+        for (int b = 0; b < NB2; b++) {
+            const bool act = (b < NV) ? hasU : hasX;
+            if (act) {
+                const double ll = in.it[(R::LAM + b) * LANES], lu = in.it[(R::LAM + NB2 + b) * LANES];
+                const double tl = in.it[(R::T + b) * LANES], tu = in.it[(R::T + NB2 + b) * LANES];
+                const double zb = (b < NV) ? in.it[(R::Z + b) * LANES] : in.it[(R::Z + NU + 3 + b) * LANES];
+                const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
+                const double rd_l = in.lin[(R::DLB + b) * LANES] - zb + tl, rd_u = -in.lin[(R::DUB + b) * LANES] + zb + tu;
+                double rm_l = ll * tl - o.tau_min, rm_u = lu * tu - o.tau_min;
+                if (delta) {
+                    rm_l += mcw * in.st[(R::MC + b) * LANES] - sigmu;
+                    rm_u += mcw * in.st[(R::MC + NB2 + b) * LANES] - sigmu;
                 }
-            }
-            if (hasU) {
-                L lin;
-                load_lin(rec, tb.lti + k * 4 * NV, lin);
-                double xnew[NX];
-                apply(lin, du, dx, xnew);
-#pragma unroll
-                for (int j = 0; j < NX; j++) dx[j] = xnew[j] + (delta ? 0.0 : rec[(R::RB + j) * LANES]);
+                const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
+                const double dl_l = -(ll * dt_l + rm_l) / tl, dl_u = -(lu * dt_u + rm_u) / tu;
+                if (!delta) { out.st[(R::MC + b) * LANES] = dt_l * dl_l; out.st[(R::MC + NB2 + b) * LANES] = dt_u * dl_u; }
+                if (cy.alpha * dl_l > ll) cy.alpha = ll / dl_l;
+                if (cy.alpha * dt_l > tl) cy.alpha = tl / dt_l;
+                if (cy.alpha * dl_u > lu) cy.alpha = lu / dl_u;
+                if (cy.alpha * dt_u > tu) cy.alpha = tu / dt_u;
+                cy.S0 += ll * tl + lu * tu;
+                cy.S1 += ll * dt_l + tl * dl_l + lu * dt_u + tu * dl_u;
+                cy.S2 += dl_l * dt_l + dl_u * dt_u;
             }
         }
-        *alpha_out = -alpha;
-        S[0] = S0; S[1] = S1; S[2] = S2;
+        if (hasU) {
+            L lin;
+            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            double xnew[NX];
+            apply(lin, du, cy.dx, xnew);
+#pragma unroll
+            for (int j = 0; j < NX; j++) cy.dx[j] = xnew[j] + (delta ? 0.0 : in.fa[(R::RB + j) * LANES]);
+        }
     }
 
-    // delta backward sweep: rhs only in the complementarity rows
-    NMPC_HD static void sweep_Bd(double* base, const Tables& tb, double sigmu, double mcw)
-    {
+    // ---- delta backward sweep: rhs only in the complementarity rows ---------------------------
+    struct CarryD {
         double dp[NX];
+        NMPC_HD void init()
+        {
 #pragma unroll
-        for (int j = 0; j < NX; j++) dp[j] = 0.0;
-        for (int k = NSTAGE; k >= 0; k--) {
-            double* rec = base + (size_t)k * R::NF * LANES;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
-            double qu[NV], qx[NX];
+            for (int j = 0; j < NX; j++) dp[j] = 0.0;
+        }
+    };
+    // reads: ST[MC], IT[T], FA[LUU,KH], LIN[E]      writes FA[LHD]
+    NMPC_HD static void stage_Bd(int k, const StageIn& in, const StageOut& out, const Tables& tb, double sigmu, double mcw, CarryD& cy)
+    {
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+        double qu[NV], qx[NX];
 #pragma unroll
-            for (int c = 0; c < NV; c++) qu[c] = 0.0;
+        for (int c = 0; c < NV; c++) qu[c] = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; j++) qx[j] = 0.0;
-            if (hasU) {
-                L lin;
-                load_lin(rec, tb.lti + k * 4 * NV, lin);
-                apply_T(lin, dp, qu, qx);
+        for (int j = 0; j < NX; j++) qx[j] = 0.0;
+        if (hasU) {
+            L lin;
+            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            apply_T(lin, cy.dp, qu, qx);
+        }
+#pragma unroll
+        for (int b = 0; b < NB2; b++) {
+            const bool act = (b < NV) ? hasU : hasX;
+            if (act) {
+                const double tl = in.it[(R::T + b) * LANES], tu = in.it[(R::T + NB2 + b) * LANES];
+                const double g = (mcw * in.st[(R::MC + b) * LANES] - sigmu) / tl - (mcw * in.st[(R::MC + NB2 + b) * LANES] - sigmu) / tu;
+                if (b < NV) qu[b] += g; else qx[3 + b] += g;
             }
+        }
+        if (hasU) {
+            double lh[NV];
 #pragma unroll
-            for (int b = 0; b < NB2; b++) {
-                const bool act = (b < NV) ? hasU : hasX;
-                if (act) {
-                    const double tl = rec[(R::T + b) * LANES], tu = rec[(R::T + NB2 + b) * LANES];
-                    const double g = (mcw * rec[(R::MC + b) * LANES] - sigmu) / tl - (mcw * rec[(R::MC + NB2 + b) * LANES] - sigmu) / tu;
-                    if (b < NV) qu[b] += g; else qx[3 + b] += g;
+            for (int a = 0; a < NV; a++) {
+                double s = qu[a];
+#pragma unroll
+                for (int c = 0; c < a; c++) s -= in.fa[(R::LUU + a * (a + 1) / 2 + c) * LANES] * lh[c];
+                lh[a] = s * in.fa[(R::LUU + a * (a + 1) / 2 + a) * LANES];
+                out.fa[(R::LHD + a) * LANES] = lh[a];
+            }
+            if (hasX) {
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+                    double s = qx[j];
+#pragma unroll
+                    for (int a = 0; a < NV; a++) s -= in.fa[(R::KH + a * NX + j) * LANES] * lh[a];
+                    cy.dp[j] = s;
                 }
             }
-            if (hasU) {
-                double lh[NV];
+        } else {
 #pragma unroll
-                for (int a = 0; a < NV; a++) {
-                    double s = qu[a];
-#pragma unroll
-                    for (int c = 0; c < a; c++) s -= rec[(R::LUU + a * (a + 1) / 2 + c) * LANES] * lh[c];
-                    lh[a] = s * rec[(R::LUU + a * (a + 1) / 2 + a) * LANES];
-                    rec[(R::LHD + a) * LANES] = lh[a];
-                }
-                if (hasX) {
-#pragma unroll
-                    for (int j = 0; j < NX; j++) {
-                        double s = qx[j];
-#pragma unroll
-                        for (int a = 0; a < NV; a++) s -= rec[(R::KH + a * NX + j) * LANES] * lh[a];
-                        dp[j] = s;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NX; j++) dp[j] = qx[j];
-            }
+            for (int j = 0; j < NX; j++) cy.dp[j] = qx[j];
         }
     }
 
     // ------------------------------------------------------------------------------------
-    // K3: the interior-point loop of one lane.  `active` false = padding lane of the last tile.
+    // K3: the interior-point loop of one lane.  `Drv` streams the stage records:
+    //   drv.template sweep<KIND>(lane_enabled, f)  calls f(k, in, out) for every stage in the
+    //   sweep's order (KIND: 0 = B first, 1 = B, 2 = F predictor, 3 = Bd, 4 = F delta).
+    // `active` false = padding lane of the last tile.
     // ------------------------------------------------------------------------------------
-    NMPC_HD static void qp_ipm_lane(double* base, const Tables& tb, const double* We, const IpmOpts& o, bool active, LaneStats& st)
+    enum { SW_B_FIRST = 0, SW_B = 1, SW_F = 2, SW_BD = 3, SW_FD = 4 };
+
+    template <class Drv>
+    NMPC_HD static void qp_ipm_lane(Drv& drv, const Tables& tb, const double* We, const IpmOpts& o, bool active, LaneStats& st)
     {
         bool done = !active;
-        double nrm[4] = {0, 0, 0, 0}, mu = 0.0, alpha = 1.0, lru = 0.0;
+        double nrm[4] = {0, 0, 0, 0}, mu = 0.0, alpha = 1.0;
         int iter = 0;
         st.lin_res = 0.0; st.cond_fallbacks = 0; st.status = 0;
-        if (!done) sweep_B(base, tb, We, o, true, 0.0, 0.0, 0.0, nrm, &mu, &lru);
+        {
+            CarryB cy; cy.init();
+            drv.template sweep<SW_B_FIRST>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+                stage_B(k, in, out, tb, We, o, true, 0.0, 0.0, 0.0, cy); });
+            nrm[0] = cy.ng; nrm[1] = cy.nb; nrm[2] = cy.nd; nrm[3] = cy.nm; mu = cy.musum / (double)NCON;
+        }
         while (true) {
             if (!done) {
                 const bool more = iter < o.iter_max && alpha > o.alpha_min &&
@@ -769,15 +830,28 @@ struct Rti {
                 }
             }
             if (!NMPC_ANY(!done)) break;
-            double S[3], a_aff = 1.0, sigmu = 0.0, mu_aff0 = 0.0;
-            if (!done) {
-                sweep_F(base, tb, o, false, 0.0, 0.0, &a_aff, S);
-                mu_aff0 = (S[0] + a_aff * (S[1] + a_aff * S[2])) / (double)NCON;
+            double S[3] = {0, 0, 0}, a_aff = 1.0, sigmu = 0.0, mu_aff0 = 0.0;
+            {
+                CarryF cy; cy.init();
+                drv.template sweep<SW_F>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+                    stage_F(k, in, out, tb, o, false, 0.0, 0.0, cy); });
+                a_aff = -cy.alpha;
+                mu_aff0 = (cy.S0 + a_aff * (cy.S1 + a_aff * cy.S2)) / (double)NCON;
                 const double r = mu_aff0 / mu;
                 sigmu = r * r * r * mu;
                 sigmu = sigmu > o.tau_min ? sigmu : o.tau_min;
-                sweep_Bd(base, tb, sigmu, 1.0);
-                sweep_F(base, tb, o, true, sigmu, 1.0, &alpha, S);
+            }
+            {
+                CarryD cy; cy.init();
+                drv.template sweep<SW_BD>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+                    stage_Bd(k, in, out, tb, sigmu, 1.0, cy); });
+            }
+            {
+                CarryF cy; cy.init();
+                drv.template sweep<SW_FD>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+                    stage_F(k, in, out, tb, o, true, sigmu, 1.0, cy); });
+                alpha = done ? alpha : -cy.alpha;
+                S[0] = cy.S0; S[1] = cy.S1; S[2] = cy.S2;
             }
             double mcw = 1.0;
             bool fb = false;
@@ -785,20 +859,31 @@ struct Rti {
                 const double mu_c = (S[0] + alpha * (S[1] + alpha * S[2])) / (double)NCON;
                 fb = mu_c > 2.0 * mu_aff0;
             }
-            if (NMPC_ANY(fb)) {
-                if (fb) {   // pure centering direction
-                    mcw = 0.0;
-                    st.cond_fallbacks++;
-                    sweep_Bd(base, tb, sigmu, 0.0);
-                    sweep_F(base, tb, o, true, sigmu, 0.0, &alpha, S);
+            if (NMPC_ANY(fb)) {   // pure centering direction for the lanes that need it
+                if (fb) { mcw = 0.0; st.cond_fallbacks++; }
+                {
+                    CarryD cy; cy.init();
+                    drv.template sweep<SW_BD>(fb, [&](int k, const StageIn& in, const StageOut& out) {
+                        stage_Bd(k, in, out, tb, sigmu, 0.0, cy); });
+                }
+                {
+                    CarryF cy; cy.init();
+                    drv.template sweep<SW_FD>(fb, [&](int k, const StageIn& in, const StageOut& out) {
+                        stage_F(k, in, out, tb, o, true, sigmu, 0.0, cy); });
+                    if (fb) alpha = -cy.alpha;
                 }
             }
             double a = alpha;
             if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-            if (!done) {
-                iter++;
-                sweep_B(base, tb, We, o, false, a, sigmu, mcw, nrm, &mu, &lru);
-                st.lin_res = fmax(st.lin_res, lru);
+            if (!done) iter++;
+            {
+                CarryB cy; cy.init();
+                drv.template sweep<SW_B>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+                    stage_B(k, in, out, tb, We, o, false, a, sigmu, mcw, cy); });
+                if (!done) {
+                    nrm[0] = cy.ng; nrm[1] = cy.nb; nrm[2] = cy.nd; nrm[3] = cy.nm; mu = cy.musum / (double)NCON;
+                    st.lin_res = fmax(st.lin_res, cy.lru);
+                }
             }
         }
         st.iter = iter;
@@ -809,15 +894,33 @@ struct Rti {
 
     // ------------------------------------------------------------------------------------
     // K4: full step x += dx, u += du for one (instance, stage); x_0 is restored to x0bar.
+    // `it` = IT record of the stage.
     // ------------------------------------------------------------------------------------
-    NMPC_HD static void step_stage(int k, const double* rec, const double* x0bar, double* xk, double* uk)
+    NMPC_HD static void step_stage(int k, const double* it, const double* x0bar, double* xk, double* uk)
     {
         if (k < NSTAGE) {
 #pragma unroll
-            for (int c = 0; c < NU; c++) uk[c] += rec[(R::Z + c) * LANES];
+            for (int c = 0; c < NU; c++) uk[c] += it[(R::Z + c) * LANES];
         }
 #pragma unroll
-        for (int j = 0; j < NX; j++) xk[j] = (k == 0) ? x0bar[j] : xk[j] + rec[(R::Z + NU + j) * LANES];
+        for (int j = 0; j < NX; j++) xk[j] = (k == 0) ? x0bar[j] : xk[j] + it[(R::Z + NU + j) * LANES];
+    }
+};
+
+// Plain driver: every stage view points straight into the tile (host emulation, and the
+// device fallback used for debugging).  The sweep body runs only for enabled lanes.
+template <int NV>
+struct DirectDriver {
+    double* tile_lane;
+    template <int KIND, class F>
+    NMPC_HD void sweep(bool enabled, F&& f)
+    {
+        if (!enabled) return;
+        const bool backward = (KIND == 0 || KIND == 1 || KIND == 3);
+        for (int s = 0; s <= NSTAGE; s++) {
+            const int k = backward ? NSTAGE - s : s;
+            f(k, tile_stage_in<NV>(tile_lane, k), tile_stage_out<NV>(tile_lane, k));
+        }
     }
 };
 

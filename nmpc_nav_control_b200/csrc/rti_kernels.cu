@@ -1,0 +1,739 @@
+// libnmpc_b200.so — sm_100a kernels and the batched C ABI (include/nmpc_b200.h).
+//
+// Kernels (one thread = one OCP instance; a warp owns a contiguous "tile" of 32 instances):
+//   k_lti_setup  : closed RK4 sensitivities of the lag/integrator rows, per stage (set-up, tiny)
+//   k_linearize  : K1 (RK4 + forward sensitivities) + K2 (Gauss-Newton LS gradient), thread per
+//                  (instance, stage) -> writes the QP records of the tile workspace
+//   k_qp_ipm     : K3, Riccati-based primal-dual interior point, thread per instance
+//   k_step       : K4, full SQP-RTI step (+ optional shift), thread per (instance, stage)
+// There is no CPU path in this library: without a CUDA device nmpc_create fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "rti_core.cuh"
+#include "pipe.cuh"
+#include "../../include/nmpc_b200.h"
+
+using namespace nmpc;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+#define CK(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return set_err(NMPC_E_CUDA, #call, e_);      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <class M>
+__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti)
+{
+    using S = Rti<M>;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= NSTAGE) return;
+    double x0[S::NX], u0[S::NU], xn[S::NX], Ep[3][S::NC], pk[S::NP], out[4 * S::NV];
+    for (int i = 0; i < S::NX; i++) x0[i] = 0.0;
+    for (int i = 0; i < S::NU; i++) u0[i] = 0.0;
+    for (int i = 0; i < S::NP; i++) pk[i] = p[k * S::NP + i];
+    S::rk4_sens(x0, u0, pk, dt, xn, Ep, out);
+    for (int i = 0; i < 4 * S::NV; i++) lti[k * 4 * S::NV + i] = out[i];
+}
+
+constexpr int LIN_BLOCK = 128;
+
+// grid: (ceil(nchunk/LIN_BLOCK), N+1).  i0 = first instance of the chunk.
+template <class M>
+__global__ void __launch_bounds__(LIN_BLOCK)
+k_linearize(int B, int i0, int nchunk, const double* __restrict__ x0bar, const double* __restrict__ yref, int nyref,
+            const double* __restrict__ We_inst, const double* __restrict__ x, const double* __restrict__ u, int ld,
+            Tables tb, double* __restrict__ ws)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    const int i = i0 + li, k = blockIdx.y;
+    double* tl = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
+    double* lin = tl + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES;
+    double* it = tl + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
+    double xk[S::NX], uk[S::NU], xk1[S::NX], yr[S::NY], xb[S::NX], We[S::NX];
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) xk[j] = x[((size_t)k * S::NX + j) * ld + i];
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) xk1[j] = x[((size_t)(k + 1) * S::NX + j) * ld + i];
+    } else {
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i] : tb.We[j];
+    }
+    for (int j = 0; j < nyref; j++) yr[j] = yref[((size_t)k * nyref + j) * B + i];
+    if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) xb[j] = x0bar[(size_t)j * B + i];
+    }
+    S::linearize_stage(k, xk, uk, xk1, yr, nyref, xb, tb, We, lin, it);
+}
+
+// K3.  One warp per CTA = one tile; dynamic shared memory = two stage slots + two mbarriers.
+// STREAM = true: bulk-async-copy pipeline (pipe.cuh); false: plain global loads (debug / A-B).
+template <class M, bool STREAM>
+__global__ void __launch_bounds__(LANES)
+k_qp_ipm(int B, int i0, int nchunk, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
+         int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int li = blockIdx.x * LANES + lane;
+    const bool active = li < nchunk;
+    const int i = i0 + li;
+    double We[S::NX];
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) We[j] = (active && We_inst) ? We_inst[(size_t)j * B + i] : tb.We[j];
+    double* tile = ws + (size_t)blockIdx.x * R::tile_doubles;
+    typename S::LaneStats st;
+    if (STREAM) {
+        using D = TmaDriver<S::NV>;
+        D drv;
+        drv.tile = tile;
+        drv.smem = reinterpret_cast<double*>(smem_raw);
+        drv.bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * (size_t)D::SLOT_FIELDS * LANES * sizeof(double));
+        drv.parity = 0; drv.lane = lane;
+        if (lane == 0) { mbar_init(&drv.bars[0], 1); mbar_init(&drv.bars[1], 1); fence_mbar_init(); }
+        __syncwarp();
+        S::qp_ipm_lane(drv, tb, We, o, active, st);
+    } else {
+        DirectDriver<S::NV> drv{tile + lane};
+        S::qp_ipm_lane(drv, tb, We, o, active, st);
+    }
+    if (active) {
+        qp_status[i] = st.status;
+        qp_iter[i] = st.iter;
+        if (stats) {
+            stats[0 * (size_t)B + i] = st.res[0]; stats[1 * (size_t)B + i] = st.res[1];
+            stats[2 * (size_t)B + i] = st.res[2]; stats[3 * (size_t)B + i] = st.res[3];
+            stats[4 * (size_t)B + i] = st.mu;     stats[5 * (size_t)B + i] = st.lin_res;
+            stats[6 * (size_t)B + i] = (double)st.cond_fallbacks; stats[7 * (size_t)B + i] = (double)st.status;
+        }
+    }
+}
+
+// K4: x += dx, u += du (acados ocp_nlp_update_variables_sqp with alpha = 1).
+// A QP that failed other than by max-iter leaves the iterate untouched and yields status 4.
+template <class M>
+__global__ void __launch_bounds__(LIN_BLOCK)
+k_step(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __restrict__ x, double* __restrict__ u, int ld,
+       const double* __restrict__ ws, const int* __restrict__ qp_status, int* __restrict__ status)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    const int i = i0 + li, k = blockIdx.y;
+    const int qs = qp_status[i];
+    if (qs != 0 && qs != 1) { if (k == 0) status[i] = NMPC_QP_FAILURE; return; }
+    const double* rec = ws + (size_t)(li / LANES) * R::tile_doubles + R::OFF_IT + (size_t)k * R::NF_IT * LANES + (li % LANES);
+    double xk[S::NX], uk[S::NU], xb[S::NX];
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { xk[j] = x[((size_t)k * S::NX + j) * ld + i]; xb[j] = (k == 0) ? x0bar[(size_t)j * B + i] : 0.0; }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
+    }
+    S::step_stage(k, rec, xb, xk, uk);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { x[((size_t)k * S::NX + j) * ld + i] = xk[j]; bad |= (xk[j] != xk[j]); }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) u[((size_t)k * S::NU + c) * ld + i] = uk[c];
+    }
+    if (bad) atomicMax(&status[i], NMPC_NAN_DETECTED);
+}
+
+__global__ void k_fill_int(int n, int* a, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// instance-major [B][R] -> SoA [R][B] (and back), 32x32 tiles through shared memory
+__global__ void k_aos_to_soa(int B, int R, const double* __restrict__ in, double* __restrict__ out)
+{
+    __shared__ double t[32][33];
+    const int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int b = b0 + y, r = r0 + threadIdx.x;
+        if (b < B && r < R) t[y][threadIdx.x] = in[(size_t)b * R + r];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y, b = b0 + threadIdx.x;
+        if (b < B && r < R) out[(size_t)r * B + b] = t[threadIdx.x][y];
+    }
+}
+// SoA with leading dim ld [R][ld] -> instance-major [B][R]
+__global__ void k_soa_to_aos(int B, int R, int ld, const double* __restrict__ in, double* __restrict__ out)
+{
+    __shared__ double t[32][33];
+    const int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y, b = b0 + threadIdx.x;
+        if (b < B && r < R) t[y][threadIdx.x] = in[(size_t)r * ld + b];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int b = b0 + y, r = r0 + threadIdx.x;
+        if (b < B && r < R) out[(size_t)b * R + r] = t[threadIdx.x][y];
+    }
+}
+// instance-major [B][R] -> SoA with leading dim ld
+__global__ void k_aos_to_soa_ld(int B, int R, int ld, const double* __restrict__ in, double* __restrict__ out)
+{
+    __shared__ double t[32][33];
+    const int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int b = b0 + y, r = r0 + threadIdx.x;
+        if (b < B && r < R) t[y][threadIdx.x] = in[(size_t)b * R + r];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y, b = b0 + threadIdx.x;
+        if (b < B && r < R) out[(size_t)r * ld + b] = t[threadIdx.x][y];
+    }
+}
+// default iterate of a freshly created solver: x_k = x0_default for all k, u = 0
+__global__ void k_init_iterate(int cap, int nx, int nu, const double* __restrict__ x0def, double* x, double* u)
+{
+    const size_t n = (size_t)cap * (NSTAGE + 1) * nx;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        x[t] = x0def[(t / cap) % nx];
+    const size_t m = (size_t)cap * NSTAGE * nu;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (size_t)gridDim.x * blockDim.x) u[t] = 0.0;
+}
+
+// fp64 FMA peak: 8 independent chains per thread
+__global__ void k_dfma(int iters, double* out)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct ModelInfo {
+    int nx, nu, np, nv;
+    double p[3], Q[11], Rw[4], QN[11], lbx[4], ubx[4], lbu[4], ubu[4];
+};
+static const double DEG = 3.14159265358979323846 / 180.0;
+// config/nmpc_nav_control_acados_models.yaml:2-75 through scripts/<m>/generate_c_code.py:30-60
+static const ModelInfo g_models[3] = {
+    {7, 2, 2, 2, {0.270, 0.1, 0}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
+     {-1, -1}, {1, 1}, {-2, -2}, {2, 2}},
+    {11, 4, 2, 4, {0.535, 0.1, 0}, {10, 10, 10, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 1, 1}, {10, 10, 10, 0, 0, 0, 0, 0, 0, 0, 0},
+     {-1, -1, -1, -1}, {1, 1, 1, 1}, {-1, -1, -1, -1}, {1, 1, 1, 1}},
+    {7, 2, 3, 2, {0.270, 0.1, 0.5}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
+     {-1, -30.0 * DEG}, {1, 30.0 * DEG}, {-1, -120.0 * DEG}, {1, 120.0 * DEG}},
+};
+
+struct nmpc_solver {
+    int model, cap, device, chunk;
+    bool stream_k3 = true;
+    ModelInfo mi;
+    nmpc_ipm_opts opts;
+    // host mirrors of the tables
+    std::vector<double> W, We, lbx, ubx, lbu, ubu, p;
+    // device
+    double *d_tab = nullptr;      // W | We | lbx | ubx | lbu | ubu | p | lti
+    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, tab_doubles;
+    bool tab_dirty = true, p_dirty = true;
+    double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
+    double *d_ws = nullptr;                      // tile workspace for one chunk
+    size_t tile_doubles = 0;
+    int *d_qp_status = nullptr;
+    // host-call staging
+    double *d_stage_in = nullptr, *d_x0bar = nullptr, *d_yref = nullptr, *d_We = nullptr, *d_out = nullptr, *d_out_aos = nullptr;
+    int *d_status = nullptr, *d_iter = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> ev;                 // 4 per chunk + 2
+    int n_ev_chunks = 0;
+    int last_chunks = 0, last_launches = 0;
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+};
+
+extern "C" int nmpc_dims(int model, nmpc_dims_t* out)
+{
+    if (model < 0 || model > 2 || !out) return set_err(NMPC_E_ARG, "nmpc_dims: bad model");
+    const ModelInfo& m = g_models[model];
+    out->nx = m.nx; out->nu = m.nu; out->np = m.np; out->ny = m.nx + m.nu; out->nyn = m.nx;
+    out->nbx = m.nv; out->nbu = m.nv; out->n = NSTAGE;
+    return 0;
+}
+
+extern "C" void nmpc_default_opts(nmpc_ipm_opts* o)
+{
+    o->mu0 = 1.0; o->alpha_min = 1e-8;
+    o->res_g_max = 1e-6; o->res_b_max = 1e-8; o->res_d_max = 1e-8; o->res_m_max = 1e-8;
+    o->reg_prim = 1e-15; o->lam_min = 1e-16; o->t_min = 1e-16; o->tau_min = 1e-16; o->thr0 = 0.1;
+    o->iter_max = 50; o->cond_pred_corr = 1;
+}
+
+extern "C" const char* nmpc_last_error(void) { return g_err; }
+
+static size_t tile_doubles_of(int model)
+{
+    switch (model) {
+        case 0: return Rec<2>::tile_doubles;
+        case 1: return Rec<4>::tile_doubles;
+        default: return Rec<2>::tile_doubles;
+    }
+}
+
+extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** out)
+{
+    if (model < 0 || model > 2 || max_batch < 1 || !out) return set_err(NMPC_E_ARG, "nmpc_create: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(NMPC_E_NODEVICE, "nmpc_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(NMPC_E_ARG, "nmpc_create: bad device index");
+    CK(cudaSetDevice(device));
+    nmpc_solver* s = new (std::nothrow) nmpc_solver();
+    if (!s) return set_err(NMPC_E_ARG, "nmpc_create: out of host memory");
+    s->model = model; s->cap = max_batch; s->device = device; s->mi = g_models[model];
+    nmpc_default_opts(&s->opts);
+    const ModelInfo& m = s->mi;
+    const int nx = m.nx, nu = m.nu, ny = nx + nu, nv = m.nv, n = NSTAGE;
+    s->W.resize((size_t)n * ny); s->We.assign(m.QN, m.QN + nx);
+    s->lbx.resize((size_t)n * nv); s->ubx.resize((size_t)n * nv); s->lbu.resize((size_t)n * nv); s->ubu.resize((size_t)n * nv);
+    s->p.resize((size_t)n * m.np);
+    for (int k = 0; k < n; k++) {
+        for (int j = 0; j < nx; j++) s->W[(size_t)k * ny + j] = m.Q[j];
+        for (int c = 0; c < nu; c++) s->W[(size_t)k * ny + nx + c] = m.Rw[c];
+        for (int c = 0; c < nv; c++) {
+            s->lbx[(size_t)k * nv + c] = m.lbx[c]; s->ubx[(size_t)k * nv + c] = m.ubx[c];
+            s->lbu[(size_t)k * nv + c] = m.lbu[c]; s->ubu[(size_t)k * nv + c] = m.ubu[c];
+        }
+        for (int q = 0; q < m.np; q++) s->p[(size_t)k * m.np + q] = m.p[q];
+    }
+    size_t off = 0;
+    s->off_W = off; off += (size_t)n * ny;
+    s->off_We = off; off += nx;
+    s->off_lbx = off; off += (size_t)n * nv;
+    s->off_ubx = off; off += (size_t)n * nv;
+    s->off_lbu = off; off += (size_t)n * nv;
+    s->off_ubu = off; off += (size_t)n * nv;
+    s->off_p = off; off += (size_t)n * m.np;
+    s->off_lti = off; off += (size_t)n * 4 * nv;
+    s->tab_doubles = off;
+    // chunking bounds the workspace: NMPC_CHUNK instances per launch group (multiple of 32)
+    int chunk = 131072;
+    if (const char* e = getenv("NMPC_CHUNK")) { int v = atoi(e); if (v >= 32) chunk = v; }
+    chunk = (chunk + LANES - 1) / LANES * LANES;
+    if (const char* e = getenv("NMPC_K3_DIRECT")) s->stream_k3 = !(atoi(e) != 0);
+    const int cap_pad = (max_batch + LANES - 1) / LANES * LANES;
+    s->chunk = chunk < cap_pad ? chunk : cap_pad;
+    s->tile_doubles = tile_doubles_of(model);
+    cudaError_t e;
+#define CKC(call) do { e = (call); if (e != cudaSuccess) { set_err(NMPC_E_CUDA, #call, e); nmpc_destroy(s); return NMPC_E_CUDA; } } while (0)
+    CKC(cudaMalloc(&s->d_tab, s->tab_doubles * sizeof(double)));
+    CKC(cudaMalloc(&s->d_x, (size_t)max_batch * (n + 1) * nx * sizeof(double)));
+    CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
+    CKC(cudaMalloc(&s->d_ws, (size_t)(s->chunk / LANES) * s->tile_doubles * sizeof(double)));
+    CKC(cudaMalloc(&s->d_qp_status, (size_t)max_batch * sizeof(int)));
+    CKC(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&s->ev_total[0])); CKC(cudaEventCreate(&s->ev_total[1]));
+    {   // default iterate: x_k = default x0 (scripts/<m>/generate_c_code.py:58-60), u = 0
+        double x0def[11] = {0, 0, 3.14159265358979323846, 0, 0, 0, 0, 0, 0, 0, 0};
+        double* d_def = s->d_tab;   // scratch: tables are uploaded later
+        CKC(cudaMemcpy(d_def, x0def, sizeof(double) * nx, cudaMemcpyHostToDevice));
+        k_init_iterate<<<1024, 256>>>(max_batch, nx, nu, d_def, s->d_x, s->d_u);
+        CKC(cudaGetLastError());
+        CKC(cudaDeviceSynchronize());
+    }
+#undef CKC
+    *out = s;
+    return 0;
+}
+
+extern "C" int nmpc_destroy(nmpc_solver* s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
+    cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
+    cudaFree(s->d_status); cudaFree(s->d_iter);
+    for (auto e : s->ev) cudaEventDestroy(e);
+    if (s->ev_total[0]) cudaEventDestroy(s->ev_total[0]);
+    if (s->ev_total[1]) cudaEventDestroy(s->ev_total[1]);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return 0;
+}
+
+extern "C" int nmpc_set_weights(nmpc_solver* s, const double* W_diag, const double* We_diag)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    if (W_diag) s->W.assign(W_diag, W_diag + s->W.size());
+    if (We_diag) s->We.assign(We_diag, We_diag + s->We.size());
+    s->tab_dirty = true;
+    return 0;
+}
+extern "C" int nmpc_set_bounds(nmpc_solver* s, const double* lbx, const double* ubx, const double* lbu, const double* ubu)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    if (lbx) s->lbx.assign(lbx, lbx + s->lbx.size());
+    if (ubx) s->ubx.assign(ubx, ubx + s->ubx.size());
+    if (lbu) s->lbu.assign(lbu, lbu + s->lbu.size());
+    if (ubu) s->ubu.assign(ubu, ubu + s->ubu.size());
+    s->tab_dirty = true;
+    return 0;
+}
+extern "C" int nmpc_set_params(nmpc_solver* s, const double* p)
+{
+    if (!s || !p) return set_err(NMPC_E_ARG, "null argument");
+    s->p.assign(p, p + s->p.size());
+    s->tab_dirty = true; s->p_dirty = true;
+    return 0;
+}
+extern "C" int nmpc_set_opts(nmpc_solver* s, const nmpc_ipm_opts* o)
+{
+    if (!s || !o) return set_err(NMPC_E_ARG, "null argument");
+    if (o->iter_max < 0 || o->iter_max > 1000) return set_err(NMPC_E_ARG, "iter_max out of range");
+    s->opts = *o;
+    return 0;
+}
+extern "C" int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o)
+{
+    if (!s || !o) return set_err(NMPC_E_ARG, "null argument");
+    *o = s->opts;
+    return 0;
+}
+
+template <class M>
+static int launch_lti(nmpc_solver* s, cudaStream_t st)
+{
+    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int upload_tables(nmpc_solver* s, cudaStream_t st)
+{
+    if (!s->tab_dirty) return 0;
+    std::vector<double> h(s->tab_doubles - (size_t)NSTAGE * 4 * s->mi.nv);
+    memcpy(&h[s->off_W], s->W.data(), s->W.size() * 8);
+    memcpy(&h[s->off_We], s->We.data(), s->We.size() * 8);
+    memcpy(&h[s->off_lbx], s->lbx.data(), s->lbx.size() * 8);
+    memcpy(&h[s->off_ubx], s->ubx.data(), s->ubx.size() * 8);
+    memcpy(&h[s->off_lbu], s->lbu.data(), s->lbu.size() * 8);
+    memcpy(&h[s->off_ubu], s->ubu.data(), s->ubu.size() * 8);
+    memcpy(&h[s->off_p], s->p.data(), s->p.size() * 8);
+    // synchronous copy from a pageable temporary: tables change rarely (set-up, or W_e per tick at batch 1)
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(s->d_tab, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    if (s->p_dirty) {
+        int rc = s->model == 0 ? launch_lti<DiffModel>(s, st) : s->model == 1 ? launch_lti<Omni4Model>(s, st) : launch_lti<TricModel>(s, st);
+        if (rc) return rc;
+        s->p_dirty = false;
+    }
+    s->tab_dirty = false;
+    return 0;
+}
+
+static Tables make_tables(const nmpc_solver* s)
+{
+    Tables tb;
+    tb.W = s->d_tab + s->off_W; tb.We = s->d_tab + s->off_We;
+    tb.lbx = s->d_tab + s->off_lbx; tb.ubx = s->d_tab + s->off_ubx;
+    tb.lbu = s->d_tab + s->off_lbu; tb.ubu = s->d_tab + s->off_ubu;
+    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti;
+    tb.dt = 1.0 / 40.0;
+    return tb;
+}
+
+static IpmOpts to_core_opts(const nmpc_ipm_opts& a)
+{
+    IpmOpts o;
+    o.mu0 = a.mu0; o.alpha_min = a.alpha_min; o.res_g_max = a.res_g_max; o.res_b_max = a.res_b_max;
+    o.res_d_max = a.res_d_max; o.res_m_max = a.res_m_max; o.reg_prim = a.reg_prim; o.lam_min = a.lam_min;
+    o.t_min = a.t_min; o.tau_min = a.tau_min; o.thr0 = a.thr0; o.iter_max = a.iter_max; o.cond_pred_corr = a.cond_pred_corr;
+    return o;
+}
+
+static int ensure_events(nmpc_solver* s, int nchunks)
+{
+    while (s->n_ev_chunks < nchunks) {
+        for (int q = 0; q < 4; q++) { cudaEvent_t e; CK(cudaEventCreate(&e)); s->ev.push_back(e); }
+        s->n_ev_chunks++;
+    }
+    return 0;
+}
+
+template <class M>
+static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
+                          double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st)
+{
+    const Tables tb = make_tables(s);
+    const IpmOpts o = to_core_opts(s->opts);
+    const int nchunks = (B + s->chunk - 1) / s->chunk;
+    int rc = ensure_events(s, nchunks);
+    if (rc) return rc;
+    s->last_chunks = nchunks; s->last_launches = 0;
+    k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
+    s->last_launches++;
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * s->chunk;
+        const int n = (B - i0) < s->chunk ? (B - i0) : s->chunk;
+        cudaEvent_t* ev = &s->ev[(size_t)c * 4];
+        CK(cudaEventRecord(ev[0], st));
+        dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
+        k_linearize<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
+        CK(cudaEventRecord(ev[1], st));
+        const int ntiles = (n + LANES - 1) / LANES;
+        if (s->stream_k3) {
+            const size_t smem = TmaDriver<M::NV>::SMEM_BYTES;
+            static bool attr_set = false;
+            if (!attr_set) {
+                CK(cudaFuncSetAttribute(k_qp_ipm<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            k_qp_ipm<M, true><<<ntiles, LANES, smem, st>>>(B, i0, n, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
+        } else {
+            k_qp_ipm<M, false><<<ntiles, LANES, 0, st>>>(B, i0, n, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
+        }
+        CK(cudaEventRecord(ev[2], st));
+        k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
+        CK(cudaEventRecord(ev[3], st));
+        s->last_launches += 3;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref,
+                                     const double* d_We, double* d_x, double* d_u, int ldxu,
+                                     int* d_status, int* d_qp_iter, double* d_stats, void* stream)
+{
+    if (!s || !d_x0bar || !d_yref || !d_status || !d_qp_iter) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_rti_solve_device: batch exceeds capacity");
+    const int ny = s->mi.nx + s->mi.nu;
+    if (nyref != 3 && nyref != ny) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: nyref must be 3 or ny");
+    if ((d_x == nullptr) != (d_u == nullptr)) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: pass both d_x and d_u or neither");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
+    int rc = upload_tables(s, st);
+    if (rc) return rc;
+    if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
+    if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
+    CK(cudaEventRecord(s->ev_total[0], st));
+    switch (s->model) {
+        case 0: rc = solve_device_t<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+        case 1: rc = solve_device_t<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+        default: rc = solve_device_t<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(s->ev_total[1], st));
+    return 0;
+}
+
+extern "C" int nmpc_iterate_device(nmpc_solver* s, double** d_x, double** d_u, int* leading_dim)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    if (d_x) *d_x = s->d_x;
+    if (d_u) *d_u = s->d_u;
+    if (leading_dim) *leading_dim = s->cap;
+    return 0;
+}
+
+extern "C" int nmpc_reset(nmpc_solver* s)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->d_x, 0, (size_t)s->cap * (NSTAGE + 1) * s->mi.nx * sizeof(double), s->own_stream));
+    CK(cudaMemsetAsync(s->d_u, 0, (size_t)s->cap * NSTAGE * s->mi.nu * sizeof(double), s->own_stream));
+    CK(cudaStreamSynchronize(s->own_stream));
+    return 0;
+}
+
+extern "C" int nmpc_reset_async(nmpc_solver* s, void* stream)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the default stream
+    CK(cudaMemsetAsync(s->d_x, 0, (size_t)s->cap * (NSTAGE + 1) * s->mi.nx * sizeof(double), st));
+    CK(cudaMemsetAsync(s->d_u, 0, (size_t)s->cap * NSTAGE * s->mi.nu * sizeof(double), st));
+    return 0;
+}
+
+static int ensure_staging(nmpc_solver* s)
+{
+    if (s->d_stage_in) return 0;
+    const int nx = s->mi.nx, nu = s->mi.nu, ny = nx + nu;
+    const size_t cap = s->cap;
+    const size_t in_rows = (size_t)(NSTAGE + 1) * nx > (size_t)(NSTAGE + 1) * ny ? (size_t)(NSTAGE + 1) * nx : (size_t)(NSTAGE + 1) * ny;
+    CK(cudaMalloc(&s->d_stage_in, cap * in_rows * sizeof(double)));
+    CK(cudaMalloc(&s->d_x0bar, cap * nx * sizeof(double)));
+    CK(cudaMalloc(&s->d_yref, cap * (NSTAGE + 1) * ny * sizeof(double)));
+    CK(cudaMalloc(&s->d_We, cap * nx * sizeof(double)));
+    CK(cudaMalloc(&s->d_out, cap * (nx + nu) * sizeof(double)));
+    CK(cudaMalloc(&s->d_out_aos, cap * (nx + nu) * sizeof(double)));
+    CK(cudaMalloc(&s->d_status, cap * sizeof(int)));
+    CK(cudaMalloc(&s->d_iter, cap * sizeof(int)));
+    return 0;
+}
+
+static int h2d_transpose(nmpc_solver* s, int B, int R, const double* h, double* d_soa, int ld, cudaStream_t st)
+{
+    CK(cudaMemcpyAsync(s->d_stage_in, h, (size_t)B * R * sizeof(double), cudaMemcpyHostToDevice, st));
+    dim3 g((B + 31) / 32, (R + 31) / 32), b(32, 8);
+    k_aos_to_soa_ld<<<g, b, 0, st>>>(B, R, ld, s->d_stage_in, d_soa);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_set_iterate_host(nmpc_solver* s, int B, const double* x, const double* u)
+{
+    if (!s || !x || !u) return set_err(NMPC_E_ARG, "null argument");
+    if (B < 1 || B > s->cap) return set_err(NMPC_E_CAPACITY, "batch exceeds capacity");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_staging(s); if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    rc = h2d_transpose(s, B, (NSTAGE + 1) * s->mi.nx, x, s->d_x, s->cap, st); if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    rc = h2d_transpose(s, B, NSTAGE * s->mi.nu, u, s->d_u, s->cap, st); if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int nmpc_get_iterate_host(nmpc_solver* s, int B, double* x, double* u)
+{
+    if (!s || !x || !u) return set_err(NMPC_E_ARG, "null argument");
+    if (B < 1 || B > s->cap) return set_err(NMPC_E_CAPACITY, "batch exceeds capacity");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_staging(s); if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    dim3 b(32, 8);
+    {
+        const int R = (NSTAGE + 1) * s->mi.nx;
+        dim3 g((B + 31) / 32, (R + 31) / 32);
+        k_soa_to_aos<<<g, b, 0, st>>>(B, R, s->cap, s->d_x, s->d_stage_in);
+        CK(cudaMemcpyAsync(x, s->d_stage_in, (size_t)B * R * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    {
+        const int R = NSTAGE * s->mi.nu;
+        dim3 g((B + 31) / 32, (R + 31) / 32);
+        k_soa_to_aos<<<g, b, 0, st>>>(B, R, s->cap, s->d_u, s->d_stage_in);
+        CK(cudaMemcpyAsync(u, s->d_stage_in, (size_t)B * R * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
+                                   double* u0, double* x1, int* status, int* qp_iter)
+{
+    if (!s || !x0bar || !yref || !u0 || !x1 || !status || !qp_iter) return set_err(NMPC_E_ARG, "nmpc_rti_solve_host: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "batch exceeds capacity");
+    const int nx = s->mi.nx, nu = s->mi.nu, ny = nx + nu;
+    if (nyref != 3 && nyref != ny) return set_err(NMPC_E_ARG, "nyref must be 3 or ny");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_staging(s); if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    // H2D: x0bar and yref land instance-major and are transposed on the device
+    {
+        CK(cudaMemcpyAsync(s->d_out_aos, x0bar, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        dim3 g((B + 31) / 32, (nx + 31) / 32), b(32, 8);
+        k_aos_to_soa<<<g, b, 0, st>>>(B, nx, s->d_out_aos, s->d_x0bar);
+    }
+    rc = h2d_transpose(s, B, (NSTAGE + 1) * nyref, yref, s->d_yref, B, st); if (rc) return rc;
+    if (We) {
+        CK(cudaMemcpyAsync(s->d_out_aos, We, (size_t)B * nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        dim3 g((B + 31) / 32, (nx + 31) / 32), b(32, 8);
+        k_aos_to_soa<<<g, b, 0, st>>>(B, nx, s->d_out_aos, s->d_We);
+    }
+    rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, nyref, We ? s->d_We : nullptr, nullptr, nullptr, 0,
+                               s->d_status, s->d_iter, nullptr, st);
+    if (rc) return rc;
+    // D2H: u_0 and x_1 only (what the controller reads back)
+    {
+        dim3 b(32, 8);
+        dim3 g1((B + 31) / 32, (nu + 31) / 32);
+        k_soa_to_aos<<<g1, b, 0, st>>>(B, nu, s->cap, s->d_u, s->d_out_aos);
+        dim3 g2((B + 31) / 32, (nx + 31) / 32);
+        k_soa_to_aos<<<g2, b, 0, st>>>(B, nx, s->cap, s->d_x + (size_t)nx * s->cap, s->d_out_aos + (size_t)B * nu);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(u0, s->d_out_aos, (size_t)B * nu * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(x1, s->d_out_aos + (size_t)B * nu, (size_t)B * nx * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status, s->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(qp_iter, s->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    s->last_launches += We ? 5 : 4;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int nmpc_last_timing(nmpc_solver* s, double* ms4)
+{
+    if (!s || !ms4) return set_err(NMPC_E_ARG, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev_total[1]));
+    double acc[3] = {0, 0, 0};
+    for (int c = 0; c < s->last_chunks; c++) {
+        cudaEvent_t* ev = &s->ev[(size_t)c * 4];
+        for (int q = 0; q < 3; q++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[q], ev[q + 1])); acc[q] += ms; }
+    }
+    float tot = 0;
+    CK(cudaEventElapsedTime(&tot, s->ev_total[0], s->ev_total[1]));
+    ms4[0] = acc[0]; ms4[1] = acc[1]; ms4[2] = acc[2]; ms4[3] = tot;
+    return 0;
+}
+
+extern "C" int nmpc_last_launches(const nmpc_solver* s) { return s ? s->last_launches : 0; }
+
+extern "C" double nmpc_dfma_peak_tflops(int device, int iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    k_dfma<<<blocks, threads>>>(iters / 10 + 1, d);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(a);
+        k_dfma<<<blocks, threads>>>(iters, d);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    return flops / (best * 1e-3) / 1e12;
+}

@@ -1,0 +1,37 @@
+"""shared test helpers (test infrastructure; may use the oracle)"""
+import numpy as np
+
+from nmpc_nav_control_b200 import synth
+from nmpc_nav_control_b200.problem import MODELS
+
+RTOL = 1e-9   # north_star: u*, x* within 1e-9 relative/absolute fp64
+ATOL = 1e-9
+
+
+def instances(name, start, count, **kw):
+    spec = MODELS[name]
+    inst = synth.make_instances(spec, start, count, **kw)
+    x0 = inst["x0"].numpy().copy()
+    yref = inst["yref"].numpy().copy()
+    We = None if inst["We"] is None else inst["We"].numpy().copy()
+    return spec, x0, yref, We
+
+
+def oracle_solve(orc, name, x0, yref, x=None, u=None, We=None, opts=None, tables=None, fast=False):
+    spec = MODELS[name]
+    B = x0.shape[0]
+    o = orc.Oracle(name, tables or spec.codegen_defaults(), fast=fast)
+    x = np.zeros((B, spec.n + 1, spec.nx)) if x is None else np.array(x, dtype=np.float64, order="C")
+    u = np.zeros((B, spec.n, spec.nu)) if u is None else np.array(u, dtype=np.float64, order="C")
+    r = o.rti_batch(np.ascontiguousarray(x0), np.ascontiguousarray(yref), x, u, opts=opts, We=We)
+    r["x"], r["u"] = x, u
+    return r
+
+
+def parity_report(a, b):
+    """per-instance worst violation of |a-b| <= ATOL + RTOL*|b|; returns (n_bad, max_abs_err)"""
+    B = a.shape[0]
+    err = np.abs(a - b).reshape(B, -1)
+    lim = (ATOL + RTOL * np.abs(b)).reshape(B, -1)
+    bad = (err > lim).any(axis=1)
+    return int(bad.sum()), float(err.max())

@@ -35,14 +35,16 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
         const double* wei = We_inst ? We_inst + (size_t)i * NX : We;
         for (int k = 0; k <= NSTAGE; k++)
             S::linearize_stage(k, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU, xi + (k < NSTAGE ? k + 1 : k) * NX,
-                               yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei, base + (size_t)k * R::NF * LANES);
+                               yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei,
+                               base + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES, base + R::OFF_IT + (size_t)k * R::NF_IT * LANES);
         typename S::LaneStats st;
-        S::qp_ipm_lane(base, tb, wei, *o, true, st);
+        DirectDriver<NV> drv{base};
+        S::qp_ipm_lane(drv, tb, wei, *o, true, st);
         status[i] = st.status; iters[i] = st.iter;
         if (stats) { for (int q = 0; q < 4; q++) stats[i * 8 + q] = st.res[q]; stats[i * 8 + 4] = st.mu; stats[i * 8 + 5] = st.lin_res; stats[i * 8 + 6] = st.cond_fallbacks; }
         if (st.status == 0 || st.status == 1)
             for (int k = 0; k <= NSTAGE; k++)
-                S::step_stage(k, base + (size_t)k * R::NF * LANES, x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
+                S::step_stage(k, base + R::OFF_IT + (size_t)k * R::NF_IT * LANES, x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
     }
     return 0;
 }

@@ -1,0 +1,121 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import instances, oracle_solve, parity_report
+from nmpc_nav_control_b200.problem import MODELS
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(name, cap):
+    from nmpc_nav_control_b200.solver import BatchedRtiSolver
+    return BatchedRtiSolver(name, cap)
+
+
+def _to_soa(a):  # [B, ...] -> [..., B] contiguous on the GPU
+    t = torch.from_numpy(a)
+    perm = list(range(1, t.dim())) + [0]
+    return t.permute(*perm).contiguous().cuda()
+
+
+@pytest.mark.parametrize("name,B", [("diff", 1000), ("omni4", 500), ("tric", 777)])
+def test_device_batch_matches_oracle(oracle_mod, name, B):
+    """ragged batch (not a multiple of 32), cold (reset) iterate, device-resident SoA inputs"""
+    spec, x0, yref, _ = instances(name, 0, B)
+    ref = oracle_solve(oracle_mod, name, x0, yref)
+    s = _solver(name, B)
+    s.reset()
+    out = s.solve_device(_to_soa(x0), _to_soa(yref), want_stats=True)
+    torch.cuda.synchronize()
+    x, u = s.get_iterate(B)
+    status = out["status"].cpu().numpy(); it = out["qp_iter"].cpu().numpy()
+    assert (status == ref["status"]).all()
+    mism = int((it != ref["qp_iter"]).sum())
+    nbx, ex = parity_report(x, ref["x"]); nbu, eu = parity_report(u, ref["u"])
+    print(f"{name}: B={B} qp_iter mismatches={mism} max|dx|={ex:.3e} max|du|={eu:.3e} "
+          f"lin_res={out['stats'][5].max().item():.2e}")
+    assert mism == 0
+    assert nbx == 0 and nbu == 0
+
+
+@pytest.mark.parametrize("name", ["diff", "omni4", "tric"])
+def test_host_call_and_warm_second_step(oracle_mod, name):
+    """controller-facing call with host buffers; a second RTI step from the persisted iterate"""
+    B = 96
+    spec, x0, yref, _ = instances(name, 5000, B, pose_only=True)
+    yfull = np.zeros((B, spec.n + 1, spec.ny)); yfull[:, :, :3] = yref
+    s = _solver(name, B)
+    s.reset()
+    out = s.solve_host(x0, yref)
+    ref = oracle_solve(oracle_mod, name, x0, yfull)
+    assert (out["status"] == 0).all() and (out["qp_iter"] == ref["qp_iter"]).all()
+    assert parity_report(out["u0"], ref["u"][:, 0])[0] == 0
+    assert parity_report(out["x1"], ref["x"][:, 1])[0] == 0
+    # second tick: x0 <- x1 (as the wrapper does, NMPCNavControlDiff.cpp:168-172), same refs
+    x0b = out["x1"].copy()
+    out2 = s.solve_host(x0b, yref)
+    ref2 = oracle_solve(oracle_mod, name, x0b, yfull, x=ref["x"], u=ref["u"])
+    assert (out2["qp_iter"] == ref2["qp_iter"]).all()
+    assert parity_report(out2["u0"], ref2["u"][:, 0])[0] == 0
+    assert parity_report(out2["x1"], ref2["x"][:, 1])[0] == 0
+
+
+def test_diff_terminal_weight_switch(oracle_mod):
+    """per-instance W_e (the diff wrapper's x1/x100 switch, NMPCNavControlDiff.cpp:127-139)"""
+    B = 200
+    spec, x0, yref, We = instances("diff", 100, B, terminal_hack=True)
+    assert We is not None and len(np.unique(We[:, 0])) == 2
+    ref = oracle_solve(oracle_mod, "diff", x0, yref, We=We)
+    s = _solver("diff", B)
+    s.reset()
+    out = s.solve_host(x0, yref, We=We)
+    assert (out["qp_iter"] == ref["qp_iter"]).all()
+    assert parity_report(out["u0"], ref["u"][:, 0])[0] == 0
+
+
+def test_smoke_case_default_iterate(oracle_mod):
+    """the codegen smoke solve (scripts/diff/generate_c_code.py:79-83): x0 = default, yref = 0,
+    iterate as created (x_k = x0 default)"""
+    for name, spec in MODELS.items():
+        x0 = np.array(spec.x0_default)[None, :]
+        yref = np.zeros((1, spec.n + 1, spec.ny))
+        xi = np.tile(x0, (1, spec.n + 1, 1)).reshape(1, spec.n + 1, spec.nx)
+        ref = oracle_solve(oracle_mod, name, x0, yref, x=xi)
+        s = _solver(name, 1)
+        out = s.solve_host(x0, yref)
+        assert out["status"][0] == 0 and out["qp_iter"][0] == ref["qp_iter"][0]
+        assert parity_report(out["u0"], ref["u"][:, 0])[0] == 0
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (65,536 diff instances): size-independent properties"""
+    from nmpc_nav_control_b200 import synth
+    spec = MODELS["diff"]
+    B = 65536
+    inst = synth.make_instances(spec, 0, B, device="cuda", pose_only=True)
+    x0 = inst["x0"].t().contiguous(); yref = inst["yref"].permute(1, 2, 0).contiguous()
+    s = _solver("diff", B)
+    s.reset()
+    out = s.solve_device(x0, yref)
+    torch.cuda.synchronize()
+    assert int((out["status"] != 0).sum()) == 0
+    dx, du, ld = None, None, None
+    import ctypes as C
+    px, pu, pl = C.c_void_p(), C.c_void_p(), C.c_int()
+    s.lib.nmpc_iterate_device(s._h, C.byref(px), C.byref(pu), C.byref(pl))
+    x, u = s.get_iterate(4096)
+    # x_0 restored to the measurement; bounds respected (interior point => strictly inside)
+    assert np.abs(x[:, 0, :] - inst["x0"][:4096].cpu().numpy()).max() == 0.0
+    assert u.min() >= -2.0 - 1e-9 and u.max() <= 2.0 + 1e-9
+    assert x[:, 1:, 5:7].min() >= -1.0 - 1e-9 and x[:, 1:, 5:7].max() <= 1.0 + 1e-9
+    # sharding invariance: instance i is the same whatever batch it is solved in
+    s2 = _solver("diff", 4096)
+    s2.reset()
+    out2 = s2.solve_device(x0[:, 1000:1000 + 4096].contiguous(), yref[:, :, 1000:1000 + 4096].contiguous())
+    torch.cuda.synchronize()
+    x2, u2 = s2.get_iterate(4096)
+    xa, ua = s.get_iterate(1000 + 4096)
+    assert np.array_equal(x2, xa[1000:]) and np.array_equal(u2, ua[1000:])
+    assert torch.equal(out2["qp_iter"], out["qp_iter"][1000:1000 + 4096])
