@@ -67,6 +67,9 @@ int nmpc_destroy(nmpc_solver* s);
 int nmpc_set_weights(nmpc_solver* s, const double* W_diag, const double* We_diag);
 int nmpc_set_bounds(nmpc_solver* s, const double* lbx, const double* ubx, const double* lbu, const double* ubu);
 int nmpc_set_params(nmpc_solver* s, const double* p);
+/* read the tables back (same layouts; any pointer may be NULL = skip) */
+int nmpc_get_tables(const nmpc_solver* s, double* W_diag, double* We_diag, double* lbx, double* ubx, double* lbu, double* ubu,
+                    double* p);
 int nmpc_set_opts(nmpc_solver* s, const nmpc_ipm_opts* o);
 int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o);
 
@@ -101,6 +104,9 @@ int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const do
  * Uses and updates the solver's persisted iterate.  Synchronous. */
 int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
                         double* u0, double* x1, int* status, int* qp_iter);
+
+/* statistics of the last nmpc_rti_solve_host call, stats [8][B] (rows as d_stats above), host pointer */
+int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats);
 
 /* timing of the last nmpc_rti_solve_* call on this solver, measured with CUDA events on its
  * stream: ms[0] = K1+K2 linearise, ms[1] = K3 QP, ms[2] = K4 step, ms[3] = total incl. copies */

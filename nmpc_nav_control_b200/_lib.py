@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(PKG, "libnmpc_b200.so")
 # every symbol include/nmpc_b200.h declares
 SYMBOLS = [
     "nmpc_dims", "nmpc_default_opts", "nmpc_last_error", "nmpc_create", "nmpc_destroy",
-    "nmpc_set_weights", "nmpc_set_bounds", "nmpc_set_params", "nmpc_set_opts", "nmpc_get_opts",
+    "nmpc_set_weights", "nmpc_set_bounds", "nmpc_set_params", "nmpc_get_tables", "nmpc_set_opts", "nmpc_get_opts",
     "nmpc_iterate_device", "nmpc_reset", "nmpc_reset_async", "nmpc_set_iterate_host", "nmpc_get_iterate_host",
-    "nmpc_rti_solve_device", "nmpc_rti_solve_host", "nmpc_last_timing", "nmpc_last_launches",
+    "nmpc_rti_solve_device", "nmpc_rti_solve_host", "nmpc_last_stats_host", "nmpc_last_timing", "nmpc_last_launches",
     "nmpc_dfma_peak_tflops",
 ]
 
@@ -53,6 +53,8 @@ def load() -> C.CDLL:
         lib.nmpc_set_weights.argtypes = [vp, dp, dp]
         lib.nmpc_set_bounds.argtypes = [vp, dp, dp, dp, dp]
         lib.nmpc_set_params.argtypes = [vp, dp]
+        lib.nmpc_get_tables.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp]
+        lib.nmpc_last_stats_host.argtypes = [vp, C.c_int, dp]
         lib.nmpc_set_opts.argtypes = [vp, C.POINTER(IpmOpts)]
         lib.nmpc_get_opts.argtypes = [vp, C.POINTER(IpmOpts)]
         lib.nmpc_iterate_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]

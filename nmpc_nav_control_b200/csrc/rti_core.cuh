@@ -373,14 +373,6 @@ struct Rti {
         }
     }
 
-    struct LaneStats {
-        int status;       // hpipm-style: 0 ok, 1 max iter, 2 min step, 3 NaN
-        int iter;
-        double res[4];    // final inf norms res_g, res_b, res_d, res_m
-        double mu;
-        double lin_res;   // max over iterations of the stationarity residual of the Newton solve
-        int cond_fallbacks;
-    };
 
     // ====================================================================================
     // K3 sweeps, written as per-stage functions with explicit carries so that the device
@@ -799,97 +791,151 @@ struct Rti {
     }
 
     // ------------------------------------------------------------------------------------
-    // K3: the interior-point loop of one lane.  `Drv` streams the stage records:
-    //   drv.template sweep<KIND>(lane_enabled, f)  calls f(k, in, out) for every stage in the
-    //   sweep's order (KIND: 0 = B first, 1 = B, 2 = F predictor, 3 = Bd, 4 = F delta).
-    // `active` false = padding lane of the last tile.
+    // K3 control: the interior-point loop of one lane, cut into the phases that sit between the
+    // horizon sweeps.  One IPM iteration =
+    //     F  (predictor forward)  -> after_F   : affine step length, sigma*mu
+    //     Bd (delta backward)
+    //     Fd (delta forward)      -> after_Fd  : step length, conditional-centering test
+    //     [Bd, Fd with mcw = 0 for the lanes that fell back -> after_Fd_fallback]
+    //     B  (apply step + residuals + factorise; before_B gives the damped step) -> after_B : exit test
+    // The device runs each sweep as its own kernel over all tiles (k_sweep in rti_kernels.cu);
+    // qp_ipm_lane below strings the same phases together for one lane (host emulation).
     // ------------------------------------------------------------------------------------
     enum { SW_B_FIRST = 0, SW_B = 1, SW_F = 2, SW_BD = 3, SW_FD = 4 };
 
-    template <class Drv>
-    NMPC_HD static void qp_ipm_lane(Drv& drv, const Tables& tb, const double* We, const IpmOpts& o, bool active, LaneStats& st)
-    {
-        bool done = !active;
-        double nrm[4] = {0, 0, 0, 0}, mu = 0.0, alpha = 1.0;
-        int iter = 0;
-        st.lin_res = 0.0; st.cond_fallbacks = 0; st.status = 0;
+    struct LaneCtl {
+        double nrm[4], mu, alpha, sigmu, mu_aff0, lin_res, mcw;
+        int done, iter, status, fb, nfb;
+        NMPC_HD void init(bool active)
         {
+            nrm[0] = nrm[1] = nrm[2] = nrm[3] = 0.0; mu = 0.0; alpha = 1.0; sigmu = 0.0; mu_aff0 = 0.0; lin_res = 0.0; mcw = 1.0;
+            done = active ? 0 : 1; iter = 0; status = 0; fb = 0; nfb = 0;
+        }
+    };
+
+    // exit test of HPIPM's main loop, evaluated right after the residuals
+    NMPC_HD static void after_B(LaneCtl& c, const CarryB& cy, const IpmOpts& o, bool first)
+    {
+        c.nrm[0] = cy.ng; c.nrm[1] = cy.nb; c.nrm[2] = cy.nd; c.nrm[3] = cy.nm; c.mu = cy.musum / (double)NCON;
+        if (!first) c.lin_res = fmax(c.lin_res, cy.lru);
+        const bool more = c.iter < o.iter_max && c.alpha > o.alpha_min &&
+                          (c.nrm[0] > o.res_g_max || c.nrm[1] > o.res_b_max || c.nrm[2] > o.res_d_max ||
+                           fabs(c.nrm[3] - o.tau_min) > o.res_m_max);
+        if (!more || c.mu != c.mu) {
+            c.done = 1;
+            c.status = (c.mu != c.mu) ? 3 : (c.iter >= o.iter_max ? 1 : (c.alpha <= o.alpha_min ? 2 : 0));
+        }
+    }
+    NMPC_HD static void after_F(LaneCtl& c, const CarryF& cy, const IpmOpts& o)
+    {
+        const double a_aff = -cy.alpha;
+        c.mu_aff0 = (cy.S0 + a_aff * (cy.S1 + a_aff * cy.S2)) / (double)NCON;
+        const double r = c.mu_aff0 / c.mu;
+        const double sm = r * r * r * c.mu;
+        c.sigmu = sm > o.tau_min ? sm : o.tau_min;
+    }
+    NMPC_HD static void after_Fd(LaneCtl& c, const CarryF& cy, const IpmOpts& o)
+    {
+        c.alpha = -cy.alpha;
+        c.mcw = 1.0;
+        c.fb = 0;
+        if (o.cond_pred_corr) {
+            const double mu_c = (cy.S0 + c.alpha * (cy.S1 + c.alpha * cy.S2)) / (double)NCON;
+            c.fb = mu_c > 2.0 * c.mu_aff0 ? 1 : 0;
+        }
+    }
+    NMPC_HD static void after_Fd_fallback(LaneCtl& c, const CarryF& cy)
+    {
+        c.alpha = -cy.alpha;
+        c.mcw = 0.0;
+        c.nfb++;
+    }
+    // damped step of HPIPM's UPDATE_VAR_QP; also counts the iteration
+    NMPC_HD static double before_B(LaneCtl& c)
+    {
+        double a = c.alpha;
+        if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+        c.iter++;
+        return a;
+    }
+
+    struct LaneStats {
+        int status;       // hpipm-style: 0 ok, 1 max iter, 2 min step, 3 NaN
+        int iter;
+        double res[4];    // final inf norms res_g, res_b, res_d, res_m
+        double mu;
+        double lin_res;   // max over iterations of the stationarity residual of the Newton solve
+        int cond_fallbacks;
+    };
+
+    // one sweep of one lane straight over its tile (lane-resolved base pointer)
+    template <int KIND, class F>
+    NMPC_HD static void sweep_lane(double* tile_lane, F&& f)
+    {
+        constexpr bool backward = (KIND == SW_B_FIRST || KIND == SW_B || KIND == SW_BD);
+#pragma unroll 1
+        for (int s = 0; s <= NSTAGE; s++) {
+            const int k = backward ? NSTAGE - s : s;
+            f(k, tile_stage_in<NV>(tile_lane, k), tile_stage_out<NV>(tile_lane, k));
+        }
+    }
+
+    // the phases run by one sweep kernel for one lane; `fallback` selects the mcw = 0 pass of Bd/Fd
+    template <int KIND>
+    NMPC_HD static void run_phase(double* tile_lane, const Tables& tb, const double* We, const IpmOpts& o, bool fallback, LaneCtl& c)
+    {
+        if (KIND == SW_B_FIRST) {
+            if (c.done) return;
             CarryB cy; cy.init();
-            drv.template sweep<SW_B_FIRST>(!done, [&](int k, const StageIn& in, const StageOut& out) {
+            sweep_lane<SW_B_FIRST>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
                 stage_B(k, in, out, tb, We, o, true, 0.0, 0.0, 0.0, cy); });
-            nrm[0] = cy.ng; nrm[1] = cy.nb; nrm[2] = cy.nd; nrm[3] = cy.nm; mu = cy.musum / (double)NCON;
+            after_B(c, cy, o, true);
+        } else if (KIND == SW_F) {
+            if (c.done) return;
+            CarryF cy; cy.init();
+            sweep_lane<SW_F>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
+                stage_F(k, in, out, tb, o, false, 0.0, 0.0, cy); });
+            after_F(c, cy, o);
+        } else if (KIND == SW_BD) {
+            if (fallback ? !c.fb : c.done) return;
+            CarryD cy; cy.init();
+            const double mcw = fallback ? 0.0 : 1.0;
+            sweep_lane<SW_BD>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
+                stage_Bd(k, in, out, tb, c.sigmu, mcw, cy); });
+        } else if (KIND == SW_FD) {
+            if (fallback ? !c.fb : c.done) return;
+            CarryF cy; cy.init();
+            const double mcw = fallback ? 0.0 : 1.0;
+            sweep_lane<SW_FD>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
+                stage_F(k, in, out, tb, o, true, c.sigmu, mcw, cy); });
+            if (fallback) after_Fd_fallback(c, cy); else after_Fd(c, cy, o);
+        } else {
+            if (c.done) return;
+            const double a = before_B(c);
+            CarryB cy; cy.init();
+            sweep_lane<SW_B>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
+                stage_B(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy); });
+            after_B(c, cy, o, false);
         }
-        while (true) {
-            if (!done) {
-                const bool more = iter < o.iter_max && alpha > o.alpha_min &&
-                                  (nrm[0] > o.res_g_max || nrm[1] > o.res_b_max || nrm[2] > o.res_d_max ||
-                                   fabs(nrm[3] - o.tau_min) > o.res_m_max);
-                if (!more || mu != mu) {
-                    done = true;
-                    st.status = (mu != mu) ? 3 : (iter >= o.iter_max ? 1 : (alpha <= o.alpha_min ? 2 : 0));
-                }
+    }
+
+    // whole IPM of one lane (host emulation of the kernel sequence)
+    NMPC_HD static void qp_ipm_lane(double* tile_lane, const Tables& tb, const double* We, const IpmOpts& o, LaneStats& st)
+    {
+        LaneCtl c; c.init(true);
+        run_phase<SW_B_FIRST>(tile_lane, tb, We, o, false, c);
+        while (!c.done) {
+            run_phase<SW_F>(tile_lane, tb, We, o, false, c);
+            run_phase<SW_BD>(tile_lane, tb, We, o, false, c);
+            run_phase<SW_FD>(tile_lane, tb, We, o, false, c);
+            if (c.fb) {
+                run_phase<SW_BD>(tile_lane, tb, We, o, true, c);
+                run_phase<SW_FD>(tile_lane, tb, We, o, true, c);
             }
-            if (!NMPC_ANY(!done)) break;
-            double S[3] = {0, 0, 0}, a_aff = 1.0, sigmu = 0.0, mu_aff0 = 0.0;
-            {
-                CarryF cy; cy.init();
-                drv.template sweep<SW_F>(!done, [&](int k, const StageIn& in, const StageOut& out) {
-                    stage_F(k, in, out, tb, o, false, 0.0, 0.0, cy); });
-                a_aff = -cy.alpha;
-                mu_aff0 = (cy.S0 + a_aff * (cy.S1 + a_aff * cy.S2)) / (double)NCON;
-                const double r = mu_aff0 / mu;
-                sigmu = r * r * r * mu;
-                sigmu = sigmu > o.tau_min ? sigmu : o.tau_min;
-            }
-            {
-                CarryD cy; cy.init();
-                drv.template sweep<SW_BD>(!done, [&](int k, const StageIn& in, const StageOut& out) {
-                    stage_Bd(k, in, out, tb, sigmu, 1.0, cy); });
-            }
-            {
-                CarryF cy; cy.init();
-                drv.template sweep<SW_FD>(!done, [&](int k, const StageIn& in, const StageOut& out) {
-                    stage_F(k, in, out, tb, o, true, sigmu, 1.0, cy); });
-                alpha = done ? alpha : -cy.alpha;
-                S[0] = cy.S0; S[1] = cy.S1; S[2] = cy.S2;
-            }
-            double mcw = 1.0;
-            bool fb = false;
-            if (!done && o.cond_pred_corr) {
-                const double mu_c = (S[0] + alpha * (S[1] + alpha * S[2])) / (double)NCON;
-                fb = mu_c > 2.0 * mu_aff0;
-            }
-            if (NMPC_ANY(fb)) {   // pure centering direction for the lanes that need it
-                if (fb) { mcw = 0.0; st.cond_fallbacks++; }
-                {
-                    CarryD cy; cy.init();
-                    drv.template sweep<SW_BD>(fb, [&](int k, const StageIn& in, const StageOut& out) {
-                        stage_Bd(k, in, out, tb, sigmu, 0.0, cy); });
-                }
-                {
-                    CarryF cy; cy.init();
-                    drv.template sweep<SW_FD>(fb, [&](int k, const StageIn& in, const StageOut& out) {
-                        stage_F(k, in, out, tb, o, true, sigmu, 0.0, cy); });
-                    if (fb) alpha = -cy.alpha;
-                }
-            }
-            double a = alpha;
-            if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
-            if (!done) iter++;
-            {
-                CarryB cy; cy.init();
-                drv.template sweep<SW_B>(!done, [&](int k, const StageIn& in, const StageOut& out) {
-                    stage_B(k, in, out, tb, We, o, false, a, sigmu, mcw, cy); });
-                if (!done) {
-                    nrm[0] = cy.ng; nrm[1] = cy.nb; nrm[2] = cy.nd; nrm[3] = cy.nm; mu = cy.musum / (double)NCON;
-                    st.lin_res = fmax(st.lin_res, cy.lru);
-                }
-            }
+            run_phase<SW_B>(tile_lane, tb, We, o, false, c);
         }
-        st.iter = iter;
-        st.mu = mu;
-#pragma unroll
-        for (int q = 0; q < 4; q++) st.res[q] = nrm[q];
+        st.status = c.status; st.iter = c.iter; st.mu = c.mu; st.lin_res = c.lin_res; st.cond_fallbacks = c.nfb;
+        for (int q = 0; q < 4; q++) st.res[q] = c.nrm[q];
     }
 
     // ------------------------------------------------------------------------------------
@@ -904,23 +950,6 @@ struct Rti {
         }
 #pragma unroll
         for (int j = 0; j < NX; j++) xk[j] = (k == 0) ? x0bar[j] : xk[j] + it[(R::Z + NU + j) * LANES];
-    }
-};
-
-// Plain driver: every stage view points straight into the tile (host emulation, and the
-// device fallback used for debugging).  The sweep body runs only for enabled lanes.
-template <int NV>
-struct DirectDriver {
-    double* tile_lane;
-    template <int KIND, class F>
-    NMPC_HD void sweep(bool enabled, F&& f)
-    {
-        if (!enabled) return;
-        const bool backward = (KIND == 0 || KIND == 1 || KIND == 3);
-        for (int s = 0; s <= NSTAGE; s++) {
-            const int k = backward ? NSTAGE - s : s;
-            f(k, tile_stage_in<NV>(tile_lane, k), tile_stage_out<NV>(tile_lane, k));
-        }
     }
 };
 

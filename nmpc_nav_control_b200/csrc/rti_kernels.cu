@@ -4,7 +4,10 @@
 //   k_lti_setup  : closed RK4 sensitivities of the lag/integrator rows, per stage (set-up, tiny)
 //   k_linearize  : K1 (RK4 + forward sensitivities) + K2 (Gauss-Newton LS gradient), thread per
 //                  (instance, stage) -> writes the QP records of the tile workspace
-//   k_qp_ipm     : K3, Riccati-based primal-dual interior point, thread per instance
+//   k_sweep<KIND>: K3, Riccati-based primal-dual interior point, thread per instance.  One launch =
+//                  one horizon sweep (factorise / predictor / delta-backward / delta-forward) of
+//                  every instance that is still iterating; the host enqueues the sweeps of all
+//                  iterations back to back, finished instances and finished launches fall through
 //   k_step       : K4, full SQP-RTI step (+ optional shift), thread per (instance, stage)
 // There is no CPU path in this library: without a CUDA device nmpc_create fails.
 #include <cuda_runtime.h>
@@ -15,7 +18,6 @@
 #include <vector>
 
 #include "rti_core.cuh"
-#include "pipe.cuh"
 #include "../../include/nmpc_b200.h"
 
 using namespace nmpc;
@@ -87,48 +89,89 @@ k_linearize(int B, int i0, int nchunk, const double* __restrict__ x0bar, const d
     S::linearize_stage(k, xk, uk, xk1, yr, nyref, xb, tb, We, lin, it);
 }
 
-// K3.  One warp per CTA = one tile; dynamic shared memory = two stage slots + two mbarriers.
-// STREAM = true: bulk-async-copy pipeline (pipe.cuh); false: plain global loads (debug / A-B).
-template <class M, bool STREAM>
-__global__ void __launch_bounds__(LANES)
-k_qp_ipm(int B, int i0, int nchunk, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
-         int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats)
+// K3 control block of one chunk: per-lane scalars of the interior-point loop (SoA, leading dim ldc)
+// and per-iteration counters.  ctl_d rows: nrm[4], mu, alpha, sigmu, mu_aff0, lin_res, mcw;
+// ctl_i rows: done, iter, status, fb, nfb.
+constexpr int NCTL_D = 10, NCTL_I = 5;
+constexpr int SW_TILES = 2;            // tiles (warps) per CTA of a sweep kernel
+
+template <class S>
+__device__ __forceinline__ void ctl_load(typename S::LaneCtl& c, const double* cd, const int* ci, int ldc, int li)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) c.nrm[q] = cd[(size_t)q * ldc + li];
+    c.mu = cd[(size_t)4 * ldc + li]; c.alpha = cd[(size_t)5 * ldc + li]; c.sigmu = cd[(size_t)6 * ldc + li];
+    c.mu_aff0 = cd[(size_t)7 * ldc + li]; c.lin_res = cd[(size_t)8 * ldc + li]; c.mcw = cd[(size_t)9 * ldc + li];
+    c.done = ci[(size_t)0 * ldc + li]; c.iter = ci[(size_t)1 * ldc + li]; c.status = ci[(size_t)2 * ldc + li];
+    c.fb = ci[(size_t)3 * ldc + li]; c.nfb = ci[(size_t)4 * ldc + li];
+}
+template <class S>
+__device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* cd, int* ci, int ldc, int li)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) cd[(size_t)q * ldc + li] = c.nrm[q];
+    cd[(size_t)4 * ldc + li] = c.mu; cd[(size_t)5 * ldc + li] = c.alpha; cd[(size_t)6 * ldc + li] = c.sigmu;
+    cd[(size_t)7 * ldc + li] = c.mu_aff0; cd[(size_t)8 * ldc + li] = c.lin_res; cd[(size_t)9 * ldc + li] = c.mcw;
+    ci[(size_t)0 * ldc + li] = c.done; ci[(size_t)1 * ldc + li] = c.iter; ci[(size_t)2 * ldc + li] = c.status;
+    ci[(size_t)3 * ldc + li] = c.fb; ci[(size_t)4 * ldc + li] = c.nfb;
+}
+
+// K3, one horizon sweep for every lane of the chunk that needs it.
+//   KIND: Rti::SW_* ; fallback = 1: the pure-centering pass of Bd/Fd for lanes flagged by Fd.
+//   gate: number of lanes that need this launch (act[it] or fbc[it]); 0 -> the whole grid returns.
+//   cnt_out: counter the launch feeds (B*: lanes still iterating -> act[it+1]; Fd: fallback lanes -> fbc[it]).
+template <class M, int KIND>
+__global__ void __launch_bounds__(LANES * SW_TILES)
+k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
+        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int fallback)
 {
     using S = Rti<M>;
     using R = typename S::R;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
-    const int li = blockIdx.x * LANES + lane;
+    if (KIND != S::SW_B_FIRST && *gate == 0) return;
+    const int li = blockIdx.x * (LANES * SW_TILES) + threadIdx.x;
     const bool active = li < nchunk;
-    const int i = i0 + li;
-    double We[S::NX];
-#pragma unroll
-    for (int j = 0; j < S::NX; j++) We[j] = (active && We_inst) ? We_inst[(size_t)j * B + i] : tb.We[j];
-    double* tile = ws + (size_t)blockIdx.x * R::tile_doubles;
-    typename S::LaneStats st;
-    if (STREAM) {
-        using D = TmaDriver<S::NV>;
-        D drv;
-        drv.tile = tile;
-        drv.smem = reinterpret_cast<double*>(smem_raw);
-        drv.bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * (size_t)D::SLOT_FIELDS * LANES * sizeof(double));
-        drv.parity = 0; drv.lane = lane;
-        if (lane == 0) { mbar_init(&drv.bars[0], 1); mbar_init(&drv.bars[1], 1); fence_mbar_init(); }
-        __syncwarp();
-        S::qp_ipm_lane(drv, tb, We, o, active, st);
-    } else {
-        DirectDriver<S::NV> drv{tile + lane};
-        S::qp_ipm_lane(drv, tb, We, o, active, st);
+    typename S::LaneCtl c;
+    bool run = false;
+    if (KIND == S::SW_B_FIRST) { c.init(active); run = active; }
+    else if (active) {
+        const int flag = ctl_i[(size_t)(fallback ? 3 : 0) * ldc + li];     // fb : done
+        run = fallback ? (flag != 0) : (flag == 0);
+        if (run) ctl_load<S>(c, ctl_d, ctl_i, ldc, li);
     }
-    if (active) {
-        qp_status[i] = st.status;
-        qp_iter[i] = st.iter;
-        if (stats) {
-            stats[0 * (size_t)B + i] = st.res[0]; stats[1 * (size_t)B + i] = st.res[1];
-            stats[2 * (size_t)B + i] = st.res[2]; stats[3 * (size_t)B + i] = st.res[3];
-            stats[4 * (size_t)B + i] = st.mu;     stats[5 * (size_t)B + i] = st.lin_res;
-            stats[6 * (size_t)B + i] = (double)st.cond_fallbacks; stats[7 * (size_t)B + i] = (double)st.status;
+    if (run) {
+        double We[S::NX];
+        if (KIND == S::SW_B_FIRST || KIND == S::SW_B) {
+#pragma unroll
+            for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i0 + li] : tb.We[j];
         }
+        double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
+        S::template run_phase<KIND>(tile_lane, tb, We, o, fallback != 0, c);
+    }
+    if (active && (run || KIND == S::SW_B_FIRST)) ctl_store<S>(c, ctl_d, ctl_i, ldc, li);
+    if (KIND == S::SW_B_FIRST || KIND == S::SW_B || (KIND == S::SW_FD && !fallback)) {
+        const bool flag = run && (KIND == S::SW_FD ? c.fb != 0 : c.done == 0);
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if ((threadIdx.x & (LANES - 1)) == 0 && m) atomicAdd(cnt_out, __popc(m));
+    }
+}
+
+// end of K3: per-instance QP status / iteration count / statistics out of the control block
+__global__ void k_ipm_finish(int B, int i0, int nchunk, int ldc, const double* __restrict__ ctl_d, const int* __restrict__ ctl_i,
+                             int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats)
+{
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    const int i = i0 + li;
+    const int status = ctl_i[(size_t)2 * ldc + li];
+    qp_status[i] = status;
+    qp_iter[i] = ctl_i[(size_t)1 * ldc + li];
+    if (stats) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) stats[(size_t)q * B + i] = ctl_d[(size_t)q * ldc + li];
+        stats[(size_t)4 * B + i] = ctl_d[(size_t)4 * ldc + li];
+        stats[(size_t)5 * B + i] = ctl_d[(size_t)8 * ldc + li];
+        stats[(size_t)6 * B + i] = (double)ctl_i[(size_t)4 * ldc + li];
+        stats[(size_t)7 * B + i] = (double)status;
     }
 }
 
@@ -258,7 +301,6 @@ static const ModelInfo g_models[3] = {
 
 struct nmpc_solver {
     int model, cap, device, chunk;
-    bool stream_k3 = true;
     ModelInfo mi;
     nmpc_ipm_opts opts;
     // host mirrors of the tables
@@ -269,11 +311,16 @@ struct nmpc_solver {
     bool tab_dirty = true, p_dirty = true;
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
     double *d_ws = nullptr;                      // tile workspace for one chunk
+    double *d_ctl_d = nullptr;                   // K3 control block of one chunk
+    int *d_ctl_i = nullptr, *d_cnt = nullptr;    // d_cnt: act[iter_max+2] | fbc[iter_max+2]
+    int cnt_cap = 0;
     size_t tile_doubles = 0;
     int *d_qp_status = nullptr;
     // host-call staging
     double *d_stage_in = nullptr, *d_x0bar = nullptr, *d_yref = nullptr, *d_We = nullptr, *d_out = nullptr, *d_out_aos = nullptr;
     int *d_status = nullptr, *d_iter = nullptr;
+    double *d_stats = nullptr;                   // [8][cap] statistics of the last host call
+    int last_host_B = 0;
     cudaStream_t own_stream = nullptr;
     std::vector<cudaEvent_t> ev;                 // 4 per chunk + 2
     int n_ev_chunks = 0;
@@ -349,7 +396,6 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     int chunk = 131072;
     if (const char* e = getenv("NMPC_CHUNK")) { int v = atoi(e); if (v >= 32) chunk = v; }
     chunk = (chunk + LANES - 1) / LANES * LANES;
-    if (const char* e = getenv("NMPC_K3_DIRECT")) s->stream_k3 = !(atoi(e) != 0);
     const int cap_pad = (max_batch + LANES - 1) / LANES * LANES;
     s->chunk = chunk < cap_pad ? chunk : cap_pad;
     s->tile_doubles = tile_doubles_of(model);
@@ -360,6 +406,10 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
     CKC(cudaMalloc(&s->d_ws, (size_t)(s->chunk / LANES) * s->tile_doubles * sizeof(double)));
     CKC(cudaMalloc(&s->d_qp_status, (size_t)max_batch * sizeof(int)));
+    CKC(cudaMalloc(&s->d_ctl_d, (size_t)NCTL_D * s->chunk * sizeof(double)));
+    CKC(cudaMalloc(&s->d_ctl_i, (size_t)NCTL_I * s->chunk * sizeof(int)));
+    s->cnt_cap = 1002;
+    CKC(cudaMalloc(&s->d_cnt, (size_t)2 * s->cnt_cap * sizeof(int)));
     CKC(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&s->ev_total[0])); CKC(cudaEventCreate(&s->ev_total[1]));
     {   // default iterate: x_k = default x0 (scripts/<m>/generate_c_code.py:58-60), u = 0
@@ -380,8 +430,9 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
+    cudaFree(s->d_ctl_d); cudaFree(s->d_ctl_i); cudaFree(s->d_cnt);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
-    cudaFree(s->d_status); cudaFree(s->d_iter);
+    cudaFree(s->d_status); cudaFree(s->d_iter); cudaFree(s->d_stats);
     for (auto e : s->ev) cudaEventDestroy(e);
     if (s->ev_total[0]) cudaEventDestroy(s->ev_total[0]);
     if (s->ev_total[1]) cudaEventDestroy(s->ev_total[1]);
@@ -413,6 +464,19 @@ extern "C" int nmpc_set_params(nmpc_solver* s, const double* p)
     if (!s || !p) return set_err(NMPC_E_ARG, "null argument");
     s->p.assign(p, p + s->p.size());
     s->tab_dirty = true; s->p_dirty = true;
+    return 0;
+}
+extern "C" int nmpc_get_tables(const nmpc_solver* s, double* W_diag, double* We_diag, double* lbx, double* ubx, double* lbu,
+                               double* ubu, double* p)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    if (W_diag) memcpy(W_diag, s->W.data(), s->W.size() * 8);
+    if (We_diag) memcpy(We_diag, s->We.data(), s->We.size() * 8);
+    if (lbx) memcpy(lbx, s->lbx.data(), s->lbx.size() * 8);
+    if (ubx) memcpy(ubx, s->ubx.data(), s->ubx.size() * 8);
+    if (lbu) memcpy(lbu, s->lbu.data(), s->lbu.size() * 8);
+    if (ubu) memcpy(ubu, s->ubu.data(), s->ubu.size() * 8);
+    if (p) memcpy(p, s->p.data(), s->p.size() * 8);
     return 0;
 }
 extern "C" int nmpc_set_opts(nmpc_solver* s, const nmpc_ipm_opts* o)
@@ -509,17 +573,29 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
         dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
         k_linearize<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
         CK(cudaEventRecord(ev[1], st));
-        const int ntiles = (n + LANES - 1) / LANES;
-        if (s->stream_k3) {
-            const size_t smem = TmaDriver<M::NV>::SMEM_BYTES;
-            static bool attr_set = false;
-            if (!attr_set) {
-                CK(cudaFuncSetAttribute(k_qp_ipm<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+        {
+            using S = Rti<M>;
+            const int ldc = s->chunk;
+            const int nb = (n + LANES * SW_TILES - 1) / (LANES * SW_TILES), nt = LANES * SW_TILES;
+            int* act = s->d_cnt;                 // act[it]: lanes entering iteration it
+            int* fbc = s->d_cnt + s->cnt_cap;    // fbc[it]: lanes of iteration it that fall back to pure centering
+            CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)2 * s->cnt_cap * sizeof(int), st));
+            k_sweep<M, S::SW_B_FIRST><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 0);
+            s->last_launches++;
+            for (int it = 0; it < o.iter_max; it++) {
+                k_sweep<M, S::SW_F><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, 0);
+                k_sweep<M, S::SW_BD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, 0);
+                k_sweep<M, S::SW_FD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, fbc + it, 0);
+                if (o.cond_pred_corr) {
+                    k_sweep<M, S::SW_BD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, fbc + it, nullptr, 1);
+                    k_sweep<M, S::SW_FD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, fbc + it, nullptr, 1);
+                    s->last_launches += 2;
+                }
+                k_sweep<M, S::SW_B><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, 0);
+                s->last_launches += 4;
             }
-            k_qp_ipm<M, true><<<ntiles, LANES, smem, st>>>(B, i0, n, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
-        } else {
-            k_qp_ipm<M, false><<<ntiles, LANES, 0, st>>>(B, i0, n, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
+            k_ipm_finish<<<(n + 255) / 256, 256, 0, st>>>(B, i0, n, ldc, s->d_ctl_d, s->d_ctl_i, s->d_qp_status, d_qp_iter, d_stats);
+            s->last_launches++;
         }
         CK(cudaEventRecord(ev[2], st));
         k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
@@ -600,6 +676,7 @@ static int ensure_staging(nmpc_solver* s)
     CK(cudaMalloc(&s->d_out_aos, cap * (nx + nu) * sizeof(double)));
     CK(cudaMalloc(&s->d_status, cap * sizeof(int)));
     CK(cudaMalloc(&s->d_iter, cap * sizeof(int)));
+    CK(cudaMalloc(&s->d_stats, cap * 8 * sizeof(double)));
     return 0;
 }
 
@@ -675,8 +752,9 @@ extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, c
         k_aos_to_soa<<<g, b, 0, st>>>(B, nx, s->d_out_aos, s->d_We);
     }
     rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, nyref, We ? s->d_We : nullptr, nullptr, nullptr, 0,
-                               s->d_status, s->d_iter, nullptr, st);
+                               s->d_status, s->d_iter, s->d_stats, st);
     if (rc) return rc;
+    s->last_host_B = B;
     // D2H: u_0 and x_1 only (what the controller reads back)
     {
         dim3 b(32, 8);
@@ -692,6 +770,15 @@ extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, c
     }
     s->last_launches += We ? 5 : 4;
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats)
+{
+    if (!s || !stats) return set_err(NMPC_E_ARG, "null argument");
+    if (!s->d_stats || B < 1 || B != s->last_host_B) return set_err(NMPC_E_ARG, "nmpc_last_stats_host: no host solve of this batch size yet");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpy(stats, s->d_stats, (size_t)B * 8 * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

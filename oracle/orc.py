@@ -148,10 +148,10 @@ class Oracle:
         for a in (x0bar, yref, x, u):
             assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
         assert yref.shape == (B, ORC_N + 1, self.ny) and x.shape == (B, ORC_N + 1, self.nx) and u.shape == (B, ORC_N, self.nu)
-        status = np.zeros(B, dtype=np.int32); qp_iter = np.zeros(B, dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32); qp_iter = np.zeros(B, dtype=np.int32); lin_res = np.zeros(B)
         we = None if We is None else np.ascontiguousarray(We, dtype=np.float64)
         f = getattr(self.lib, self.pfx + "rti_batch"); f.restype = C.c_int
         used = f(_dp(self.prob), C.byref(opts), C.c_int(B), _dp(x0bar), _dp(yref), None if we is None else _dp(we),
                  _dp(x), _dp(u), status.ctypes.data_as(C.POINTER(C.c_int)), qp_iter.ctypes.data_as(C.POINTER(C.c_int)),
-                 C.c_int(nthreads))
-        return dict(status=status, qp_iter=qp_iter, threads=used)
+                 C.c_int(nthreads), _dp(lin_res))
+        return dict(status=status, qp_iter=qp_iter, threads=used, lin_res=lin_res)

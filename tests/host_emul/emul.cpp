@@ -38,8 +38,7 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
                                yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei,
                                base + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES, base + R::OFF_IT + (size_t)k * R::NF_IT * LANES);
         typename S::LaneStats st;
-        DirectDriver<NV> drv{base};
-        S::qp_ipm_lane(drv, tb, wei, *o, true, st);
+        S::qp_ipm_lane(base, tb, wei, *o, st);
         status[i] = st.status; iters[i] = st.iter;
         if (stats) { for (int q = 0; q < 4; q++) stats[i * 8 + q] = st.res[q]; stats[i * 8 + 4] = st.mu; stats[i * 8 + 5] = st.lin_res; stats[i * 8 + 6] = st.cond_fallbacks; }
         if (st.status == 0 || st.status == 1)
