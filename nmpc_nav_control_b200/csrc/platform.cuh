@@ -24,6 +24,22 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #endif
 }
 
+// per-lane scratch columns live in shared memory on the device, interleaved over the threads of a
+// sweep CTA (bank-conflict free); the host emulation uses a plain array
+#if defined(__CUDACC__)
+#define NMPC_SCRATCH_STRIDE 64
+#else
+#define NMPC_SCRATCH_STRIDE 1
+#endif
+
+// keeps the compiler from hoisting the loads of a later phase of a stage above an earlier one
+// (register pressure); no instruction is emitted
+#if defined(__CUDA_ARCH__)
+#define NMPC_PHASE_FENCE() asm volatile("" ::: "memory")
+#else
+#define NMPC_PHASE_FENCE() ((void)0)
+#endif
+
 constexpr int LANES = 32;     // instances per tile = lanes per warp
 constexpr int NSTAGE = 80;    // N: scripts/<m>/common.py:5-9 (tf_ini=2.0, freq=40)
 

@@ -133,6 +133,7 @@ struct Rti {
     static constexpr int NV = M::NV, NP = M::NP, NX = 3 + 2 * NV, NU = NV, NZ = NX + NU, NY = NZ;
     static constexpr int NC = 1 + 3 * NV, NB2 = 2 * NV, NPK = NX * (NX + 1) / 2, NLU = NV * (NV + 1) / 2;
     static constexpr int NCON = 2 * (NV + (NSTAGE - 1) * NB2 + NV);   // one-sided constraints
+    static constexpr int PSTRIDE = NMPC_SCRATCH_STRIDE;               // element stride of the per-lane scratch column
     using R = Rec<NV>;
     using L = Lin<NV>;
 
@@ -380,25 +381,68 @@ struct Rti {
     // ====================================================================================
 
     // ---- B sweep: (apply previous step) + residuals + Riccati factorisation, stage N..0 -----
+    // All vectors and matrices carried from stage to stage live in a per-lane scratch column `sc`
+    // (shared memory on the device, element stride PSTRIDE; a plain array in the host emulation):
+    // the cost-to-go matrix P (packed symmetric, double-buffered because the Schur complement of a
+    // stage reads all of the successor's P), its gradient pv, and the three vectors of the
+    // update / adjoint recursion.  Registers only carry the norm accumulators.  The stage body is
+    // cut in two phases (update + residuals, then Riccati) so that neither holds the other's data.
     struct CarryB {
-        double P[NPK], pv[NX], pi_o[NX], dpi[NX], xn[NX];
+        static constexpr int SC_P = 0, SC_PV = 2 * NPK, SC_PIO = SC_PV + NX, SC_DPI = SC_PIO + NX, SC_XN = SC_DPI + NX,
+                             SC_N = SC_XN + NX;
+        double* sc;
+        int cur;          // which P buffer holds the successor's cost-to-go
         double ng, nb, nd, nm, musum, lru;
-        NMPC_HD void init()
+        NMPC_HD void init(double* scratch)
         {
+            sc = scratch; cur = 0;
 #pragma unroll
-            for (int i = 0; i < NX; i++) { pv[i] = 0.0; pi_o[i] = 0.0; dpi[i] = 0.0; xn[i] = 0.0; }
-#pragma unroll
-            for (int i = 0; i < NPK; i++) P[i] = 0.0;
+            for (int i = SC_PV; i < SC_N; i++) sc[i * PSTRIDE] = 0.0;
             ng = nb = nd = nm = musum = lru = 0.0;
         }
     };
-    // reads : LIN[all], IT[all], ST[DZ, MC] (not when first)      writes: IT[all], FA[LUU,KH,LH,RB]
-    NMPC_HD static void stage_B(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
-                                const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy)
+    // g = P * (column j of [B A]), P read from the scratch column
+    NMPC_HD static void P_col_s(const double* P, const L& l, int j, double* g)
     {
+#define PP(i, m) P[pk(i, m) * PSTRIDE]
+        if (j < NV) {
+            const int c = j;
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+                g[i] = PP(i, 0) * l.E[0][1 + 2 * NV + c] + PP(i, 1) * l.E[1][1 + 2 * NV + c] + PP(i, 2) * l.E[2][1 + 2 * NV + c]
+                     + PP(i, 3 + c) * l.au[c] + PP(i, 3 + NV + c) * l.ru[c];
+        } else if (j < NV + 2) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) g[i] = PP(i, j - NV);
+        } else if (j == NV + 2) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) g[i] = PP(i, 0) * l.E[0][0] + PP(i, 1) * l.E[1][0] + PP(i, 2) * l.E[2][0];
+        } else if (j < NV + 3 + NV) {
+            const int c = j - NV - 3;
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+                g[i] = PP(i, 0) * l.E[0][1 + c] + PP(i, 1) * l.E[1][1 + c] + PP(i, 2) * l.E[2][1 + c] + PP(i, 3 + c) * l.av[c];
+        } else {
+            const int c = j - NV - 3 - NV;
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+                g[i] = PP(i, 0) * l.E[0][1 + NV + c] + PP(i, 1) * l.E[1][1 + NV + c] + PP(i, 2) * l.E[2][1 + NV + c]
+                     + PP(i, 3 + c) * l.ar[c] + PP(i, 3 + NV + c);
+        }
+#undef PP
+    }
+
+    // phase 1 of a B stage: apply the previous step, evaluate the residuals, store the iterate.
+    // Leaves the stage gradient (incl. barrier terms) in gu/gx, the dynamics residual in rb and the
+    // barrier Hessian terms in Gam.
+    // reads : LIN[all], IT[all], ST[DZ, MC] (not when first)      writes: IT[all]
+    NMPC_HD static void stage_B_update(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+                                       const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
+                                       double* gu, double* gx, double* rb, double* Gam)
+    {
+        using C = CarryB;
         const bool hasU = k < NSTAGE, hasX = k > 0;
-        L lin;
-        if (hasU) load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+        double* sc = cy.sc;
         double Hu[NV], Hx[NX], qu[NV], qx[NX];
 #pragma unroll
         for (int c = 0; c < NV; c++) { Hu[c] = hasU ? tb.dt * tb.W[k * NY + NX + c] : 0.0; qu[c] = in.lin[(R::Q + c) * LANES]; }
@@ -410,9 +454,15 @@ struct Rti {
 #pragma unroll
         for (int b = 0; b < NB2; b++) { dl[b] = in.lin[(R::DLB + b) * LANES]; du_[b] = in.lin[(R::DUB + b) * LANES]; }
 
+        L lin;
         double v1u[NV], v1x[NX], v2u[NV], v2x[NX];
-        if (hasU) { apply_T(lin, cy.pi_o, v1u, v1x); apply_T(lin, cy.dpi, v2u, v2x); }
-        else {
+        if (hasU) {
+            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            double pio[NX], dpi[NX];
+#pragma unroll
+            for (int j = 0; j < NX; j++) { pio[j] = sc[(C::SC_PIO + j) * PSTRIDE]; dpi[j] = sc[(C::SC_DPI + j) * PSTRIDE]; }
+            apply_T(lin, pio, v1u, v1x); apply_T(lin, dpi, v2u, v2x);
+        } else {
 #pragma unroll
             for (int c = 0; c < NV; c++) { v1u[c] = 0.0; v2u[c] = 0.0; }
 #pragma unroll
@@ -440,6 +490,8 @@ struct Rti {
                     tl[b] = t_l; tu[b] = t_u; ll[b] = o.mu0 / t_l; lu[b] = o.mu0 / t_u;
                 } else { tl[b] = 1.0; tu[b] = 1.0; ll[b] = 0.0; lu[b] = 0.0; }
             }
+#pragma unroll
+            for (int j = 0; j < NX; j++) sc[(C::SC_DPI + j) * PSTRIDE] = 0.0;
         } else {
             double dzu[NV], dzx[NX];
 #pragma unroll
@@ -488,7 +540,7 @@ struct Rti {
                 for (int j = 0; j < NX; j++) {
                     double r = qx[j] + Hx[j] * zx[j] - pin[j] + v1x[j] + Hx[j] * dzx[j] + v2x[j];
                     if (j >= 3 + NV) r += ldo[j - 3] - dld[j - 3];
-                    cy.dpi[j] = r;
+                    sc[(C::SC_DPI + j) * PSTRIDE] = r;
                     pin[j] += a_step * r;
                     zx[j] += a_step * dzx[j];
                 }
@@ -498,25 +550,26 @@ struct Rti {
         }
 
         // ---- residuals at the (new) iterate -----------------------------------------------
-        double rgu[NV], rgx[NX], rb[NX];
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            rgu[c] = qu[c] + Hu[c] * zu[c] + (lu[c] - ll[c]) + (v1u[c] + a_step * v2u[c]);
-            if (hasU) cy.ng = fmax(cy.ng, fabs(rgu[c]));
+            gu[c] = qu[c] + Hu[c] * zu[c] + (lu[c] - ll[c]) + (v1u[c] + a_step * v2u[c]);
+            if (hasU) cy.ng = fmax(cy.ng, fabs(gu[c]));
         }
 #pragma unroll
         for (int j = 0; j < NX; j++) {
             double r = qx[j] + Hx[j] * zx[j] - pin[j] + (v1x[j] + a_step * v2x[j]);
             if (j >= 3 + NV) r += lu[j - 3] - ll[j - 3];
-            rgx[j] = r;
+            gx[j] = r;
             if (hasX) cy.ng = fmax(cy.ng, fabs(r));
         }
         if (hasU) {
             apply(lin, zu, zx, rb);
 #pragma unroll
-            for (int i = 0; i < NX; i++) { rb[i] += in.lin[(R::B0 + i) * LANES] - cy.xn[i]; cy.nb = fmax(cy.nb, fabs(rb[i])); }
+            for (int i = 0; i < NX; i++) {
+                rb[i] += in.lin[(R::B0 + i) * LANES] - sc[(C::SC_XN + i) * PSTRIDE];
+                cy.nb = fmax(cy.nb, fabs(rb[i]));
+            }
         }
-        double Gam[NB2], gam[NB2];
 #pragma unroll
         for (int b = 0; b < NB2; b++) {
             const bool act = (b < NV) ? hasU : hasX;
@@ -533,11 +586,12 @@ struct Rti {
                 const double l_l = ll[b] < o.lam_min ? o.lam_min : ll[b];
                 const double l_u = lu[b] < o.lam_min ? o.lam_min : lu[b];
                 Gam[b] = ti_l * l_l + ti_u * l_u;
-                gam[b] = ti_l * (rm_l - ll[b] * rd_l) - ti_u * (rm_u - lu[b] * rd_u);
-            } else { Gam[b] = 0.0; gam[b] = 0.0; }
+                const double gam = ti_l * (rm_l - ll[b] * rd_l) - ti_u * (rm_u - lu[b] * rd_u);
+                if (b < NV) gu[b] += gam; else gx[3 + b] += gam;
+            } else Gam[b] = 0.0;
         }
 
-        // ---- store the iterate --------------------------------------------------------------
+        // ---- store the iterate, hand the carries to stage k-1 --------------------------------
 #pragma unroll
         for (int c = 0; c < NV; c++) out.it[(R::Z + c) * LANES] = zu[c];
         if (hasX) {
@@ -549,58 +603,69 @@ struct Rti {
             out.it[(R::LAM + b) * LANES] = ll[b]; out.it[(R::LAM + NB2 + b) * LANES] = lu[b];
             out.it[(R::T + b) * LANES] = tl[b];   out.it[(R::T + NB2 + b) * LANES] = tu[b];
         }
+#pragma unroll
+        for (int j = 0; j < NX; j++) { sc[(C::SC_PIO + j) * PSTRIDE] = pi_old[j]; sc[(C::SC_XN + j) * PSTRIDE] = zx[j]; }
+    }
 
-        // ---- Riccati step -------------------------------------------------------------------
-        // gradient of the stage incl. barrier terms and the cost-to-go of the successor
-        double gu[NV], gx[NX];
-#pragma unroll
-        for (int c = 0; c < NV; c++) gu[c] = rgu[c] + gam[c];
-#pragma unroll
-        for (int j = 0; j < NX; j++) gx[j] = rgx[j] + (j >= 3 + NV ? gam[j - 3] : 0.0);
+    // phase 2 of a B stage: one step of the Riccati recursion.
+    // reads : LIN[E]      writes: FA[LUU,KH,LH,RB]
+    NMPC_HD static void stage_B_riccati(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+                                        const IpmOpts& o, CarryB& cy, double* gu, double* gx, const double* rb, const double* Gam)
+    {
+        using C = CarryB;
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+        double* sc = cy.sc;
+        const double* P = sc + (size_t)(C::SC_P + cy.cur * NPK) * PSTRIDE;         // successor's cost-to-go
+        double* Pn = sc + (size_t)(C::SC_P + (cy.cur ^ 1) * NPK) * PSTRIDE;        // this stage's
         if (hasU) {
+            L lin;
+            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
 #pragma unroll
             for (int i = 0; i < NX; i++) out.fa[(R::RB + i) * LANES] = rb[i];
-            double Pb[NX];
+            {
+                double Pb[NX];
 #pragma unroll
-            for (int i = 0; i < NX; i++) {
-                double s = cy.pv[i];
+                for (int i = 0; i < NX; i++) {
+                    double s = sc[(C::SC_PV + i) * PSTRIDE];
 #pragma unroll
-                for (int j = 0; j < NX; j++) s += cy.P[pk(i, j)] * rb[j];
-                Pb[i] = s;
+                    for (int j = 0; j < NX; j++) s += P[pk(i, j) * PSTRIDE] * rb[j];
+                    Pb[i] = s;
+                }
+                double tu_[NV], tx_[NX];
+                apply_T(lin, Pb, tu_, tx_);
+#pragma unroll
+                for (int c = 0; c < NV; c++) gu[c] += tu_[c];
+#pragma unroll
+                for (int j = 0; j < NX; j++) gx[j] += tx_[j];
             }
-            double tu_[NV], tx_[NX];
-            apply_T(lin, Pb, tu_, tx_);
+            // M = [B A]' P [B A] + diag(H + Gamma + reg), built column by column in z order [u; x].
+            // Control columns first: Muu (packed lower) and Mxu, then the Cholesky of Muu; the state
+            // columns are folded straight into this stage's P (Schur complement), one at a time.
+            double Muu[NLU], Kh[NV][NX];
 #pragma unroll
-            for (int c = 0; c < NV; c++) gu[c] += tu_[c];
-#pragma unroll
-            for (int j = 0; j < NX; j++) gx[j] += tx_[j];
-
-            // M = [B A]' P [B A] + diag(H + Gamma + reg), packed lower in z order
-            constexpr int NMK = NZ * (NZ + 1) / 2;
-            double Mk[NMK];
-#pragma unroll
-            for (int j = 0; j < NZ; j++) {
-                if (!hasX && j >= NV) break;
+            for (int a = 0; a < NV; a++) {
                 double g[NX], cu[NV], cx[NX];
-                P_col(cy.P, lin, j, g);
+                P_col_s(P, lin, a, g);
                 apply_T(lin, g, cu, cx);
 #pragma unroll
-                for (int i = j; i < NZ; i++) Mk[i * (i + 1) / 2 + j] = (i < NV) ? cu[i] : cx[i - NV];
+                for (int b = a; b < NV; b++) Muu[b * (b + 1) / 2 + a] = cu[b];
+#pragma unroll
+                for (int j = 0; j < NX; j++) Kh[a][j] = cx[j];
             }
 #pragma unroll
-            for (int c = 0; c < NV; c++) Mk[c * (c + 1) / 2 + c] += Hu[c] + o.reg_prim + Gam[c];
+            for (int c = 0; c < NV; c++) Muu[c * (c + 1) / 2 + c] += tb.dt * tb.W[k * NY + NX + c] + o.reg_prim + Gam[c];
             // Cholesky of the control block, diagonal kept inverted
             double Luu[NLU];
 #pragma unroll
             for (int a = 0; a < NV; a++) {
-                double d = Mk[a * (a + 1) / 2 + a];
+                double d = Muu[a * (a + 1) / 2 + a];
 #pragma unroll
                 for (int c = 0; c < a; c++) d -= Luu[a * (a + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
                 const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
                 Luu[a * (a + 1) / 2 + a] = inv;
 #pragma unroll
                 for (int b = a + 1; b < NV; b++) {
-                    double s = Mk[b * (b + 1) / 2 + a];
+                    double s = Muu[b * (b + 1) / 2 + a];
 #pragma unroll
                     for (int c = 0; c < a; c++) s -= Luu[b * (b + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
                     Luu[b * (b + 1) / 2 + a] = s * inv;
@@ -618,12 +683,11 @@ struct Rti {
                 out.fa[(R::LH + a) * LANES] = lh[a];
             }
             if (hasX) {
-                double Kh[NV][NX];
 #pragma unroll
                 for (int j = 0; j < NX; j++) {
 #pragma unroll
                     for (int a = 0; a < NV; a++) {
-                        double s = Mk[(NV + j) * (NV + j + 1) / 2 + a];
+                        double s = Kh[a][j];
 #pragma unroll
                         for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * Kh[c][j];
                         Kh[a][j] = s * Luu[a * (a + 1) / 2 + a];
@@ -631,36 +695,45 @@ struct Rti {
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < NX; i++) {
+                for (int j = 0; j < NX; j++) {
+                    double g[NX], cu[NV], cx[NX];
+                    P_col_s(P, lin, NV + j, g);
+                    apply_T(lin, g, cu, cx);
 #pragma unroll
-                    for (int j = 0; j <= i; j++) {
-                        double s = Mk[(NV + i) * (NV + i + 1) / 2 + NV + j];
+                    for (int i = j; i < NX; i++) {
+                        double s = cx[i];
 #pragma unroll
                         for (int a = 0; a < NV; a++) s -= Kh[a][i] * Kh[a][j];
-                        if (i == j) s += Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0);
-                        cy.P[pk(i, j)] = s;
+                        if (i == j) s += tb.dt * tb.W[k * NY + i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0);
+                        Pn[pk(i, j) * PSTRIDE] = s;
                     }
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) {
                     double s = gx[i];
 #pragma unroll
                     for (int a = 0; a < NV; a++) s -= Kh[a][i] * lh[a];
-                    cy.pv[i] = s;
+                    sc[(C::SC_PV + i) * PSTRIDE] = s;
                 }
             }
         } else {
 #pragma unroll
             for (int i = 0; i < NX; i++) {
 #pragma unroll
-                for (int j = 0; j <= i; j++) cy.P[pk(i, j)] = (i == j) ? Hx[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0) : 0.0;
-                cy.pv[i] = gx[i];
+                for (int j = 0; j <= i; j++) Pn[pk(i, j) * PSTRIDE] = (i == j) ? We[i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0) : 0.0;
+                sc[(C::SC_PV + i) * PSTRIDE] = gx[i];
             }
         }
-        // carries for stage k-1
-#pragma unroll
-        for (int j = 0; j < NX; j++) { cy.pi_o[j] = pi_old[j]; cy.xn[j] = zx[j]; }
-        if (first) {
-#pragma unroll
-            for (int j = 0; j < NX; j++) cy.dpi[j] = 0.0;
-        }
+        cy.cur ^= 1;
+    }
+
+    NMPC_HD static void stage_B(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+                                const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy)
+    {
+        double gu[NV], gx[NX], rb[NX], Gam[NB2];
+        stage_B_update(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
+        NMPC_PHASE_FENCE();
+        stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam);
     }
 
     // ---- forward sweeps.  delta == false: predictor (writes ST.DZA, ST.MC); delta == true: adds
@@ -882,11 +955,12 @@ struct Rti {
 
     // the phases run by one sweep kernel for one lane; `fallback` selects the mcw = 0 pass of Bd/Fd
     template <int KIND>
-    NMPC_HD static void run_phase(double* tile_lane, const Tables& tb, const double* We, const IpmOpts& o, bool fallback, LaneCtl& c)
+    NMPC_HD static void run_phase(double* tile_lane, const Tables& tb, const double* We, const IpmOpts& o, bool fallback, LaneCtl& c,
+                                  double* scratch)
     {
         if (KIND == SW_B_FIRST) {
             if (c.done) return;
-            CarryB cy; cy.init();
+            CarryB cy; cy.init(scratch);
             sweep_lane<SW_B_FIRST>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
                 stage_B(k, in, out, tb, We, o, true, 0.0, 0.0, 0.0, cy); });
             after_B(c, cy, o, true);
@@ -912,7 +986,7 @@ struct Rti {
         } else {
             if (c.done) return;
             const double a = before_B(c);
-            CarryB cy; cy.init();
+            CarryB cy; cy.init(scratch);
             sweep_lane<SW_B>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
                 stage_B(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy); });
             after_B(c, cy, o, false);
@@ -923,16 +997,17 @@ struct Rti {
     NMPC_HD static void qp_ipm_lane(double* tile_lane, const Tables& tb, const double* We, const IpmOpts& o, LaneStats& st)
     {
         LaneCtl c; c.init(true);
-        run_phase<SW_B_FIRST>(tile_lane, tb, We, o, false, c);
+        double scratch[CarryB::SC_N * PSTRIDE];
+        run_phase<SW_B_FIRST>(tile_lane, tb, We, o, false, c, scratch);
         while (!c.done) {
-            run_phase<SW_F>(tile_lane, tb, We, o, false, c);
-            run_phase<SW_BD>(tile_lane, tb, We, o, false, c);
-            run_phase<SW_FD>(tile_lane, tb, We, o, false, c);
+            run_phase<SW_F>(tile_lane, tb, We, o, false, c, scratch);
+            run_phase<SW_BD>(tile_lane, tb, We, o, false, c, scratch);
+            run_phase<SW_FD>(tile_lane, tb, We, o, false, c, scratch);
             if (c.fb) {
-                run_phase<SW_BD>(tile_lane, tb, We, o, true, c);
-                run_phase<SW_FD>(tile_lane, tb, We, o, true, c);
+                run_phase<SW_BD>(tile_lane, tb, We, o, true, c, scratch);
+                run_phase<SW_FD>(tile_lane, tb, We, o, true, c, scratch);
             }
-            run_phase<SW_B>(tile_lane, tb, We, o, false, c);
+            run_phase<SW_B>(tile_lane, tb, We, o, false, c, scratch);
         }
         st.status = c.status; st.iter = c.iter; st.mu = c.mu; st.lin_res = c.lin_res; st.cond_fallbacks = c.nfb;
         for (int q = 0; q < 4; q++) st.res[q] = c.nrm[q];

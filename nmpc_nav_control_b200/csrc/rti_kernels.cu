@@ -94,6 +94,7 @@ k_linearize(int B, int i0, int nchunk, const double* __restrict__ x0bar, const d
 // ctl_i rows: done, iter, status, fb, nfb.
 constexpr int NCTL_D = 10, NCTL_I = 5;
 constexpr int SW_TILES = 2;            // tiles (warps) per CTA of a sweep kernel
+static_assert(LANES * SW_TILES == NMPC_SCRATCH_STRIDE, "scratch columns are interleaved over the CTA's threads");
 
 template <class S>
 __device__ __forceinline__ void ctl_load(typename S::LaneCtl& c, const double* cd, const int* ci, int ldc, int li)
@@ -128,6 +129,9 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
     using S = Rti<M>;
     using R = typename S::R;
     if (KIND != S::SW_B_FIRST && *gate == 0) return;
+    // per-lane scratch column (cost-to-go matrix of the factorising sweeps), interleaved over the CTA
+    extern __shared__ double scratch_buf[];       // B sweeps: CarryB::SC_N columns of NMPC_SCRATCH_STRIDE doubles
+    double* scratch = scratch_buf;
     const int li = blockIdx.x * (LANES * SW_TILES) + threadIdx.x;
     const bool active = li < nchunk;
     typename S::LaneCtl c;
@@ -145,7 +149,7 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
             for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i0 + li] : tb.We[j];
         }
         double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
-        S::template run_phase<KIND>(tile_lane, tb, We, o, fallback != 0, c);
+        S::template run_phase<KIND>(tile_lane, tb, We, o, fallback != 0, c, scratch + threadIdx.x);
     }
     if (active && (run || KIND == S::SW_B_FIRST)) ctl_store<S>(c, ctl_d, ctl_i, ldc, li);
     if (KIND == S::SW_B_FIRST || KIND == S::SW_B || (KIND == S::SW_FD && !fallback)) {
@@ -579,8 +583,15 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
             const int nb = (n + LANES * SW_TILES - 1) / (LANES * SW_TILES), nt = LANES * SW_TILES;
             int* act = s->d_cnt;                 // act[it]: lanes entering iteration it
             int* fbc = s->d_cnt + s->cnt_cap;    // fbc[it]: lanes of iteration it that fall back to pure centering
+            const size_t smB = (size_t)S::CarryB::SC_N * NMPC_SCRATCH_STRIDE * sizeof(double);
+            static bool attr_set = false;         // per template instantiation (= per model)
+            if (!attr_set) {
+                CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+                CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+                attr_set = true;
+            }
             CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)2 * s->cnt_cap * sizeof(int), st));
-            k_sweep<M, S::SW_B_FIRST><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 0);
+            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 0);
             s->last_launches++;
             for (int it = 0; it < o.iter_max; it++) {
                 k_sweep<M, S::SW_F><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, 0);
@@ -591,7 +602,7 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                     k_sweep<M, S::SW_FD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, fbc + it, nullptr, 1);
                     s->last_launches += 2;
                 }
-                k_sweep<M, S::SW_B><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, 0);
+                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, 0);
                 s->last_launches += 4;
             }
             k_ipm_finish<<<(n + 255) / 256, 256, 0, st>>>(B, i0, n, ldc, s->d_ctl_d, s->d_ctl_i, s->d_qp_status, d_qp_iter, d_stats);
