@@ -871,10 +871,11 @@ struct Rti {
     //     Fd (delta forward)      -> after_Fd  : step length, conditional-centering test
     //     [Bd, Fd with mcw = 0 for the lanes that fell back -> after_Fd_fallback]
     //     B  (apply step + residuals + factorise; before_B gives the damped step) -> after_B : exit test
-    // The device runs each sweep as its own kernel over all tiles (k_sweep in rti_kernels.cu);
+    // The device runs two kernels per iteration over all tiles (k_sweep in rti_kernels.cu): FDF =
+    // the three solve sweeps (light on registers, high occupancy) and B (the factorising sweep);
     // qp_ipm_lane below strings the same phases together for one lane (host emulation).
     // ------------------------------------------------------------------------------------
-    enum { SW_B_FIRST = 0, SW_B = 1, SW_F = 2, SW_BD = 3, SW_FD = 4 };
+    enum { SW_B_FIRST = 0, SW_B = 1, SW_F = 2, SW_BD = 3, SW_FD = 4, SW_FDF = 5 };
 
     struct LaneCtl {
         double nrm[4], mu, alpha, sigmu, mu_aff0, lin_res, mcw;
@@ -983,6 +984,16 @@ struct Rti {
             sweep_lane<SW_FD>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
                 stage_F(k, in, out, tb, o, true, c.sigmu, mcw, cy); });
             if (fallback) after_Fd_fallback(c, cy); else after_Fd(c, cy, o);
+        } else if (KIND == SW_FDF) {
+            // the three solve sweeps of one iteration back to back (no lane depends on another), with
+            // the pure-centering repeat for the lanes whose corrector overshoots
+            run_phase<SW_F>(tile_lane, tb, We, o, false, c, scratch);
+            run_phase<SW_BD>(tile_lane, tb, We, o, false, c, scratch);
+            run_phase<SW_FD>(tile_lane, tb, We, o, false, c, scratch);
+            if (!c.done && c.fb) {
+                run_phase<SW_BD>(tile_lane, tb, We, o, true, c, scratch);
+                run_phase<SW_FD>(tile_lane, tb, We, o, true, c, scratch);
+            }
         } else {
             if (c.done) return;
             const double a = before_B(c);
@@ -1000,13 +1011,7 @@ struct Rti {
         double scratch[CarryB::SC_N * PSTRIDE];
         run_phase<SW_B_FIRST>(tile_lane, tb, We, o, false, c, scratch);
         while (!c.done) {
-            run_phase<SW_F>(tile_lane, tb, We, o, false, c, scratch);
-            run_phase<SW_BD>(tile_lane, tb, We, o, false, c, scratch);
-            run_phase<SW_FD>(tile_lane, tb, We, o, false, c, scratch);
-            if (c.fb) {
-                run_phase<SW_BD>(tile_lane, tb, We, o, true, c, scratch);
-                run_phase<SW_FD>(tile_lane, tb, We, o, true, c, scratch);
-            }
+            run_phase<SW_FDF>(tile_lane, tb, We, o, false, c, scratch);
             run_phase<SW_B>(tile_lane, tb, We, o, false, c, scratch);
         }
         st.status = c.status; st.iter = c.iter; st.mu = c.mu; st.lin_res = c.lin_res; st.cond_fallbacks = c.nfb;

@@ -117,19 +117,19 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
     ci[(size_t)3 * ldc + li] = c.fb; ci[(size_t)4 * ldc + li] = c.nfb;
 }
 
-// K3, one horizon sweep for every lane of the chunk that needs it.
-//   KIND: Rti::SW_* ; fallback = 1: the pure-centering pass of Bd/Fd for lanes flagged by Fd.
-//   gate: number of lanes that need this launch (act[it] or fbc[it]); 0 -> the whole grid returns.
-//   cnt_out: counter the launch feeds (B*: lanes still iterating -> act[it+1]; Fd: fallback lanes -> fbc[it]).
+// K3, one kernel = one or three horizon sweeps for every lane of the chunk that is still iterating.
+//   KIND: Rti::SW_B_FIRST (cold start + residuals + factorise), SW_FDF (predictor forward, delta
+//         backward, delta forward [+ centering repeat]), SW_B (apply step + residuals + factorise).
+//   gate: number of lanes still iterating (act[it]); 0 -> the whole grid returns at once.
+//   cnt_out (B kernels): lanes that continue -> act[it+1].
 template <class M, int KIND>
-__global__ void __launch_bounds__(LANES * SW_TILES)
+__global__ void __launch_bounds__(LANES * SW_TILES, KIND == 5 ? 8 : 4)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
-        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int fallback)
+        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out)
 {
     using S = Rti<M>;
     using R = typename S::R;
     if (KIND != S::SW_B_FIRST && *gate == 0) return;
-    // per-lane scratch column (cost-to-go matrix of the factorising sweeps), interleaved over the CTA
     extern __shared__ double scratch_buf[];       // B sweeps: CarryB::SC_N columns of NMPC_SCRATCH_STRIDE doubles
     double* scratch = scratch_buf;
     const int li = blockIdx.x * (LANES * SW_TILES) + threadIdx.x;
@@ -138,8 +138,7 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
     bool run = false;
     if (KIND == S::SW_B_FIRST) { c.init(active); run = active; }
     else if (active) {
-        const int flag = ctl_i[(size_t)(fallback ? 3 : 0) * ldc + li];     // fb : done
-        run = fallback ? (flag != 0) : (flag == 0);
+        run = ctl_i[li] == 0;                      // row 0 = done
         if (run) ctl_load<S>(c, ctl_d, ctl_i, ldc, li);
     }
     if (run) {
@@ -149,12 +148,11 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
             for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i0 + li] : tb.We[j];
         }
         double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
-        S::template run_phase<KIND>(tile_lane, tb, We, o, fallback != 0, c, scratch + threadIdx.x);
+        S::template run_phase<KIND>(tile_lane, tb, We, o, false, c, scratch + threadIdx.x);
     }
     if (active && (run || KIND == S::SW_B_FIRST)) ctl_store<S>(c, ctl_d, ctl_i, ldc, li);
-    if (KIND == S::SW_B_FIRST || KIND == S::SW_B || (KIND == S::SW_FD && !fallback)) {
-        const bool flag = run && (KIND == S::SW_FD ? c.fb != 0 : c.done == 0);
-        const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (KIND == S::SW_B_FIRST || KIND == S::SW_B) {
+        const unsigned m = __ballot_sync(0xffffffffu, run && c.done == 0);
         if ((threadIdx.x & (LANES - 1)) == 0 && m) atomicAdd(cnt_out, __popc(m));
     }
 }
@@ -316,7 +314,7 @@ struct nmpc_solver {
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
     double *d_ws = nullptr;                      // tile workspace for one chunk
     double *d_ctl_d = nullptr;                   // K3 control block of one chunk
-    int *d_ctl_i = nullptr, *d_cnt = nullptr;    // d_cnt: act[iter_max+2] | fbc[iter_max+2]
+    int *d_ctl_i = nullptr, *d_cnt = nullptr;    // d_cnt: act[iter_max+2], lanes entering iteration it
     int cnt_cap = 0;
     size_t tile_doubles = 0;
     int *d_qp_status = nullptr;
@@ -413,7 +411,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     CKC(cudaMalloc(&s->d_ctl_d, (size_t)NCTL_D * s->chunk * sizeof(double)));
     CKC(cudaMalloc(&s->d_ctl_i, (size_t)NCTL_I * s->chunk * sizeof(int)));
     s->cnt_cap = 1002;
-    CKC(cudaMalloc(&s->d_cnt, (size_t)2 * s->cnt_cap * sizeof(int)));
+    CKC(cudaMalloc(&s->d_cnt, (size_t)s->cnt_cap * sizeof(int)));
     CKC(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&s->ev_total[0])); CKC(cudaEventCreate(&s->ev_total[1]));
     {   // default iterate: x_k = default x0 (scripts/<m>/generate_c_code.py:58-60), u = 0
@@ -582,7 +580,6 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
             const int ldc = s->chunk;
             const int nb = (n + LANES * SW_TILES - 1) / (LANES * SW_TILES), nt = LANES * SW_TILES;
             int* act = s->d_cnt;                 // act[it]: lanes entering iteration it
-            int* fbc = s->d_cnt + s->cnt_cap;    // fbc[it]: lanes of iteration it that fall back to pure centering
             const size_t smB = (size_t)S::CarryB::SC_N * NMPC_SCRATCH_STRIDE * sizeof(double);
             static bool attr_set = false;         // per template instantiation (= per model)
             if (!attr_set) {
@@ -590,20 +587,13 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
                 attr_set = true;
             }
-            CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)2 * s->cnt_cap * sizeof(int), st));
-            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 0);
+            CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)s->cnt_cap * sizeof(int), st));
+            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act);
             s->last_launches++;
             for (int it = 0; it < o.iter_max; it++) {
-                k_sweep<M, S::SW_F><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, 0);
-                k_sweep<M, S::SW_BD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, 0);
-                k_sweep<M, S::SW_FD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, fbc + it, 0);
-                if (o.cond_pred_corr) {
-                    k_sweep<M, S::SW_BD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, fbc + it, nullptr, 1);
-                    k_sweep<M, S::SW_FD><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, fbc + it, nullptr, 1);
-                    s->last_launches += 2;
-                }
-                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, 0);
-                s->last_launches += 4;
+                k_sweep<M, S::SW_FDF><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr);
+                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1);
+                s->last_launches += 2;
             }
             k_ipm_finish<<<(n + 255) / 256, 256, 0, st>>>(B, i0, n, ldc, s->d_ctl_d, s->d_ctl_i, s->d_qp_status, d_qp_iter, d_stats);
             s->last_launches++;

@@ -1,0 +1,45 @@
+"""summarise an ncu --csv launch list (per-launch time, DRAM bytes, issue rate) of the solver kernels"""
+import collections
+import csv
+import re
+import sys
+
+
+def num(m, n):
+    v, u = m.get(n, ('0', ''))
+    v = float(v.replace(',', ''))
+    mult = {'ns': 1e-6, 'us': 1e-3, 'ms': 1, 's': 1e3, 'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+    return v * mult
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+    hdr = rows[hi]
+    data = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) < len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        key = (int(d['ID']), d['Kernel Name'][:80])
+        data.setdefault(key, {})[d['Metric Name']] = (d['Metric Value'], d['Metric Unit'])
+    tot = 0.0
+    names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd'}
+    for (i, k), m in data.items():
+        kind = re.search(r'k_sweep<(\w+), \(int\)(\d)>', k)
+        name = names[kind.group(2)] if kind else k[:24]
+        t = num(m, 'gpu__time_duration.sum'); rd = num(m, 'dram__bytes_read.sum'); wr = num(m, 'dram__bytes_write.sum')
+        tot += t
+        extra = ''
+        for key, lab in (('smsp__inst_executed.sum', 'inst'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'),
+                         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
+                         ('smsp__thread_inst_executed_per_inst_executed.ratio', 'thr/inst'),
+                         ('l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum', 'local_ld_B')):
+            if key in m:
+                extra += f' {lab}={num(m, key):.4g}'
+        print(f'{i:3d} {name:8s} t={t:.3f}ms rd={rd / 1e9:.2f}GB wr={wr / 1e9:.2f}GB bw={(rd + wr) / max(t, 1e-9) / 1e9:.2f}TB/s{extra}')
+    print(f'total {tot:.3f} ms over {len(data)} launches')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
