@@ -119,3 +119,22 @@ def test_full_size_properties():
     xa, ua = s.get_iterate(1000 + 4096)
     assert np.array_equal(x2, xa[1000:]) and np.array_equal(u2, ua[1000:])
     assert torch.equal(out2["qp_iter"], out["qp_iter"][1000:1000 + 4096])
+
+
+@pytest.mark.parametrize("name", ["diff", "omni4", "tric"])
+def test_golden_vectors_two_steps(name):
+    """committed fixtures (tests/golden/make_golden.py): no oracle at run time"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"rti_{name}.npz"))
+    B = g["x0"].shape[0]
+    s = _solver(name, B)
+    s.reset()
+    out = s.solve_host(np.ascontiguousarray(g["x0"]), np.ascontiguousarray(g["yref"]))
+    x, u = s.get_iterate(B)
+    assert (out["qp_iter"] == g["qp_iter"]).all() and (out["status"] == g["status"]).all()
+    assert parity_report(x, g["x"])[0] == 0 and parity_report(u, g["u"])[0] == 0
+    out2 = s.solve_host(np.ascontiguousarray(out["x1"]), np.ascontiguousarray(g["yref"]))
+    x2, u2 = s.get_iterate(B)
+    assert (out2["qp_iter"] == g["qp_iter2"]).all()
+    lr = g["lin_res2"]
+    assert parity_report(x2, g["x2"], lr)[0] == 0 and parity_report(u2, g["u2"], lr)[0] == 0
