@@ -252,6 +252,16 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # measured DRAM traffic of K3 per solve (ncu dram__bytes over all K3 launches of one step, see
+    # tools/ncu_launches.py --json and profiles/): what the streaming roofline is computed from
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("model") == MODEL and tj.get("batch") == B:
+            traffic = float(tj["dram_bytes_per_step"])
+    except Exception:
+        pass
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -282,18 +292,25 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": MODEL, "batch_per_gpu": B, "N": spec.n, "iterate": "reset (zero) before every step",
-                   "l2": "inputs (131 MB) + per-step workspace (5.6 GB) exceed the 126 MB L2; no explicit flush",
+                   "l2": "inputs (131 MB) + K3 workspace streamed every sweep (5.6 GB) exceed the 126 MB L2; no explicit flush",
                    "mean_qp_iter": mean_iter, "status_nonzero": status_bad},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "api": "nmpc_rti_solve_host (C ABI, pinned host buffers)"},
         "gpu_launches": launches,
         "kernel_ms": kt,
-        "roofline": {"kernel": "k_qp_ipm (K3)", "bound": "hbm", "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": alg_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                     "note": "achieved = algorithmic bytes (17,512 B/solve, SURVEY 8d) / K3 launch time; K3 streams its "
-                             "per-stage workspace through HBM every sweep, see roofline_fp64 and DESIGN.md"},
-        "roofline_fp64": {"kernel": "k_qp_ipm (K3)", "bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+        "roofline": {"kernel": "K3 interior point = all k_sweep<B_FIRST|FDF|B> launches of one step", "bound": "hbm",
+                     "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": alg_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                     "note": "achieved = algorithmic bytes (17,512 B/solve, SURVEY 8d) x instances / K3 time per step "
+                             "(CUDA events inside the library, on the launching stream); traffic = measured DRAM bytes of "
+                             "the same launches (ncu): K3 streams the 85 KB interior-point state of every instance "
+                             "through HBM each sweep, see roofline_stream and DESIGN.md 5"},
+        "roofline_stream": None if traffic is None else {
+            "kernel": "K3", "bound": "hbm", "achieved": traffic / qp_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": traffic / qp_s / 1e9 / hbm_peak,
+            "note": "measured DRAM traffic of the K3 launches (ncu, profiles/k3_traffic.json) / K3 time of this run"},
+        "roofline_fp64": {"kernel": "K3", "bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,
                           "peak_source": "self-measured DFMA micro-benchmark (MEASURED_PEAKS.json has no fp64 figure)",
                           "note": "achieved = dense-equivalent flops (2.69e5 per IPM iteration, SURVEY 8d) x measured mean iterations"},

@@ -12,7 +12,7 @@ def num(m, n):
     return v * mult
 
 
-def main(path):
+def main(path, json_out=None, model=None, batch=None):
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
     hdr = rows[hi]
@@ -24,12 +24,15 @@ def main(path):
         key = (int(d['ID']), d['Kernel Name'][:80])
         data.setdefault(key, {})[d['Metric Name']] = (d['Metric Value'], d['Metric Unit'])
     tot = 0.0
-    names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd'}
+    k3_bytes = 0.0; k3_ms = 0.0
+    names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd', '5': 'FDF'}
     for (i, k), m in data.items():
-        kind = re.search(r'k_sweep<(\w+), \(int\)(\d)>', k)
+        kind = re.search(r'k_sweep<([\w:]+), (?:\(int\))?(\d)>', k)
         name = names[kind.group(2)] if kind else k[:24]
         t = num(m, 'gpu__time_duration.sum'); rd = num(m, 'dram__bytes_read.sum'); wr = num(m, 'dram__bytes_write.sum')
         tot += t
+        if kind:
+            k3_bytes += rd + wr; k3_ms += t
         extra = ''
         for key, lab in (('smsp__inst_executed.sum', 'inst'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'),
                          ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
@@ -38,8 +41,16 @@ def main(path):
             if key in m:
                 extra += f' {lab}={num(m, key):.4g}'
         print(f'{i:3d} {name:8s} t={t:.3f}ms rd={rd / 1e9:.2f}GB wr={wr / 1e9:.2f}GB bw={(rd + wr) / max(t, 1e-9) / 1e9:.2f}TB/s{extra}')
-    print(f'total {tot:.3f} ms over {len(data)} launches')
+    print(f'total {tot:.3f} ms over {len(data)} launches; K3 launches: {k3_ms:.3f} ms, {k3_bytes / 1e9:.2f} GB DRAM')
+    if json_out:
+        import json
+        json.dump({"model": model, "batch": batch, "dram_bytes_per_step": k3_bytes, "k3_ms_under_ncu": k3_ms,
+                   "launches": len(data), "source": path}, open(json_out, "w"))
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    # usage: ncu_launches.py launches.csv [out.json model batch]
+    if len(sys.argv) >= 5:
+        main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]))
+    else:
+        main(sys.argv[1])
