@@ -230,6 +230,7 @@ struct Rti {
     // K2 (ocp_nlp_cost_nls with y=[x;u], scripts/<m>/generate_c_code.py:30-39): gradient
     //   s_k W (y - yref), s_k = dt for k<N and 1 for k=N; the Hessian s_k W is never stored.
     // ------------------------------------------------------------------------------------
+    template <class RR = R, int LS = LANES>
     NMPC_HD static void linearize_stage(int k, const double* xk, const double* uk, const double* xk1,
                                         const double* yref, int nyref, const double* x0bar,
                                         const Tables& tb, const double* We, double* lin, double* it)
@@ -240,41 +241,41 @@ struct Rti {
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int c = 0; c < NC; c++) lin[(R::E + i * NC + c) * LANES] = Ep[i][c];
+                for (int c = 0; c < NC; c++) lin[(RR::E + i * NC + c) * LS] = Ep[i][c];
 #pragma unroll
-            for (int i = 0; i < NX; i++) lin[(R::B0 + i) * LANES] = xn[i] - xk1[i];
+            for (int i = 0; i < NX; i++) lin[(RR::B0 + i) * LS] = xn[i] - xk1[i];
             const double* Wk = tb.W + k * NY;
 #pragma unroll
             for (int c = 0; c < NU; c++) {
                 const double yr = (NX + c < nyref) ? yref[NX + c] : 0.0;
-                lin[(R::Q + c) * LANES] = (tb.dt * Wk[NX + c]) * (uk[c] - yr);
-                lin[(R::DLB + c) * LANES] = tb.lbu[k * NV + c] - uk[c];
-                lin[(R::DUB + c) * LANES] = tb.ubu[k * NV + c] - uk[c];
+                lin[(RR::Q + c) * LS] = (tb.dt * Wk[NX + c]) * (uk[c] - yr);
+                lin[(RR::DLB + c) * LS] = tb.lbu[k * NV + c] - uk[c];
+                lin[(RR::DUB + c) * LS] = tb.ubu[k * NV + c] - uk[c];
             }
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 const double yr = (j < nyref) ? yref[j] : 0.0;
-                lin[(R::Q + NU + j) * LANES] = (tb.dt * Wk[j]) * (xk[j] - yr);
+                lin[(RR::Q + NU + j) * LS] = (tb.dt * Wk[j]) * (xk[j] - yr);
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < NU; c++) lin[(R::Q + c) * LANES] = 0.0;
+            for (int c = 0; c < NU; c++) lin[(RR::Q + c) * LS] = 0.0;
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 const double yr = (j < nyref) ? yref[j] : 0.0;
-                lin[(R::Q + NU + j) * LANES] = We[j] * (xk[j] - yr);
+                lin[(RR::Q + NU + j) * LS] = We[j] * (xk[j] - yr);
             }
         }
         if (k >= 1) {
 #pragma unroll
             for (int c = 0; c < NV; c++) {
-                lin[(R::DLB + NV + c) * LANES] = tb.lbx[(k - 1) * NV + c] - xk[3 + NV + c];
-                lin[(R::DUB + NV + c) * LANES] = tb.ubx[(k - 1) * NV + c] - xk[3 + NV + c];
+                lin[(RR::DLB + NV + c) * LS] = tb.lbx[(k - 1) * NV + c] - xk[3 + NV + c];
+                lin[(RR::DUB + NV + c) * LS] = tb.ubx[(k - 1) * NV + c] - xk[3 + NV + c];
             }
         } else {
             // x0 elimination (d_ocp_qp_reduce_eq_dof): the stage-0 state is the constant x0bar - x_0
 #pragma unroll
-            for (int j = 0; j < NX; j++) it[(R::Z + NU + j) * LANES] = x0bar[j] - xk[j];
+            for (int j = 0; j < NX; j++) it[(RR::Z + NU + j) * LS] = x0bar[j] - xk[j];
         }
     }
 
@@ -1022,14 +1023,15 @@ struct Rti {
     // K4: full step x += dx, u += du for one (instance, stage); x_0 is restored to x0bar.
     // `it` = IT record of the stage.
     // ------------------------------------------------------------------------------------
+    template <class RR = R, int LS = LANES>
     NMPC_HD static void step_stage(int k, const double* it, const double* x0bar, double* xk, double* uk)
     {
         if (k < NSTAGE) {
 #pragma unroll
-            for (int c = 0; c < NU; c++) uk[c] += it[(R::Z + c) * LANES];
+            for (int c = 0; c < NU; c++) uk[c] += it[(RR::Z + c) * LS];
         }
 #pragma unroll
-        for (int j = 0; j < NX; j++) xk[j] = (k == 0) ? x0bar[j] : xk[j] + it[(R::Z + NU + j) * LANES];
+        for (int j = 0; j < NX; j++) xk[j] = (k == 0) ? x0bar[j] : xk[j] + it[(RR::Z + NU + j) * LS];
     }
 };
 

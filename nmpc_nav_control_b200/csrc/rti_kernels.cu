@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "rti_core.cuh"
+#include "rti_group.cuh"
 #include "../../include/nmpc_b200.h"
 
 using namespace nmpc;
@@ -155,6 +156,100 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
         const unsigned m = __ballot_sync(0xffffffffu, run && c.done == 0);
         if ((threadIdx.x & (LANES - 1)) == 0 && m) atomicAdd(cnt_out, __popc(m));
     }
+}
+
+// ---- group path (rti_group.cuh): per-instance contiguous records -----------------------------
+// K1+K2 into the group layout: block = LIN_BLOCK instances of one stage; the [Q, LHD) head of every
+// record is staged in shared memory and written out as contiguous 368-byte (diff) runs.
+template <class M>
+__global__ void __launch_bounds__(LIN_BLOCK)
+k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const double* __restrict__ yref, int nyref,
+              const double* __restrict__ We_inst, const double* __restrict__ x, const double* __restrict__ u, int ld,
+              Tables tb, double* __restrict__ ws)
+{
+    using S = Rti<M>;
+    using GR = GRec<S::NV>;
+    constexpr int HEAD = GR::LHD, ROW = HEAD | 1;           // odd row stride: conflict-free column access
+    extern __shared__ double lin_sm[];
+    const int li = blockIdx.x * LIN_BLOCK + threadIdx.x, k = blockIdx.y;
+    if (li < nchunk) {
+        const int i = i0 + li;
+        double xk[S::NX], uk[S::NU], xk1[S::NX], yr[S::NY], xb[S::NX], We[S::NX];
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) xk[j] = x[((size_t)k * S::NX + j) * ld + i];
+        if (k < NSTAGE) {
+#pragma unroll
+            for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
+#pragma unroll
+            for (int j = 0; j < S::NX; j++) xk1[j] = x[((size_t)(k + 1) * S::NX + j) * ld + i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i] : tb.We[j];
+        }
+        for (int j = 0; j < nyref; j++) yr[j] = yref[((size_t)k * nyref + j) * B + i];
+        if (k == 0) {
+#pragma unroll
+            for (int j = 0; j < S::NX; j++) xb[j] = x0bar[(size_t)j * B + i];
+        }
+        double* row = lin_sm + (size_t)threadIdx.x * ROW;
+        for (int d = 0; d < HEAD; d++) row[d] = 0.0;      // stages 0 and N fill only part of the head; padding stays defined
+        S::template linearize_stage<GR, 1>(k, xk, uk, xk1, yr, nyref, xb, tb, We, row, ws + (size_t)li * GR::inst_doubles + (size_t)k * GR::NREC);
+    }
+    __syncthreads();
+    const int nrow = min(LIN_BLOCK, nchunk - blockIdx.x * LIN_BLOCK);
+    for (int idx = threadIdx.x; idx < nrow * HEAD; idx += LIN_BLOCK) {
+        const int r = idx / HEAD, d = idx - r * HEAD;
+        ws[(size_t)(blockIdx.x * LIN_BLOCK + r) * GR::inst_doubles + (size_t)k * GR::NREC + d] = lin_sm[(size_t)r * ROW + d];
+    }
+}
+
+constexpr int GRP_WARPS = 4;           // warps per CTA of the group kernel
+
+// K3, group path: persistent warps, each running the whole interior-point loop of 32/G instances at a
+// time and refilling converged slots from the queue *next (instances [0, n) of the chunk).
+template <class M, int G, int MINB>
+__global__ void __launch_bounds__(GRP_WARPS * 32, MINB)
+k_ipm_group(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldWe, IpmOpts o, double* __restrict__ ws,
+            int* __restrict__ next, GrpOut out)
+{
+    using GP = Grp<M, G>;
+    extern __shared__ __align__(16) double grp_sm[];
+    double* sm = grp_sm + (size_t)(threadIdx.x >> 5) * GP::WARP_D;
+    typename GP::Lane L;
+    GP::init_lane(L, threadIdx.x & 31);
+    GP::run_warp(&L, sm, ws, i0, n, next, tb, We_inst, ldWe, o, out);
+}
+
+// K4 from the group layout
+template <class M>
+__global__ void __launch_bounds__(LIN_BLOCK)
+k_step_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __restrict__ x, double* __restrict__ u, int ld,
+         const double* __restrict__ ws, const int* __restrict__ qp_status, int* __restrict__ status)
+{
+    using S = Rti<M>;
+    using GR = GRec<S::NV>;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    const int i = i0 + li, k = blockIdx.y;
+    const int qs = qp_status[i];
+    if (qs != 0 && qs != 1) { if (k == 0) status[i] = NMPC_QP_FAILURE; return; }
+    const double* rec = ws + (size_t)li * GR::inst_doubles + (size_t)k * GR::NREC;
+    double xk[S::NX], uk[S::NU], xb[S::NX];
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { xk[j] = x[((size_t)k * S::NX + j) * ld + i]; xb[j] = (k == 0) ? x0bar[(size_t)j * B + i] : 0.0; }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
+    }
+    S::template step_stage<GR, 1>(k, rec, xb, xk, uk);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { x[((size_t)k * S::NX + j) * ld + i] = xk[j]; bad |= (xk[j] != xk[j]); }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) u[((size_t)k * S::NU + c) * ld + i] = uk[c];
+    }
+    if (bad) atomicMax(&status[i], NMPC_NAN_DETECTED);
 }
 
 // end of K3: per-instance QP status / iteration count / statistics out of the control block
@@ -303,6 +398,9 @@ static const ModelInfo g_models[3] = {
 
 struct nmpc_solver {
     int model, cap, device, chunk;
+    int k3_group = 1;            // 1: lane-group persistent K3 (rti_group.cuh); 0: per-sweep kernels (rti_core.cuh)
+    int grp_G = 0, grp_blocks = 0;
+    size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
     nmpc_ipm_opts opts;
     // host mirrors of the tables
@@ -401,12 +499,20 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     const int cap_pad = (max_batch + LANES - 1) / LANES * LANES;
     s->chunk = chunk < cap_pad ? chunk : cap_pad;
     s->tile_doubles = tile_doubles_of(model);
+    if (const char* e = getenv("NMPC_K3")) s->k3_group = strcmp(e, "sweep") != 0;
+    s->grp_G = (model == 1) ? 16 : 8;
+    if (const char* e = getenv("NMPC_GRP_G")) { int v = atoi(e); if ((v == 8 && model != 1) || v == 16 || v == 32) s->grp_G = v; }
+    {
+        const size_t per_group = (model == 1) ? GRec<4>::inst_doubles : GRec<2>::inst_doubles;
+        const size_t per_sweep = s->tile_doubles / LANES;
+        s->ws_doubles_per_inst = s->k3_group ? per_group : per_sweep;
+    }
     cudaError_t e;
 #define CKC(call) do { e = (call); if (e != cudaSuccess) { set_err(NMPC_E_CUDA, #call, e); nmpc_destroy(s); return NMPC_E_CUDA; } } while (0)
     CKC(cudaMalloc(&s->d_tab, s->tab_doubles * sizeof(double)));
     CKC(cudaMalloc(&s->d_x, (size_t)max_batch * (n + 1) * nx * sizeof(double)));
     CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
-    CKC(cudaMalloc(&s->d_ws, (size_t)(s->chunk / LANES) * s->tile_doubles * sizeof(double)));
+    CKC(cudaMalloc(&s->d_ws, (size_t)s->chunk * s->ws_doubles_per_inst * sizeof(double)));
     CKC(cudaMalloc(&s->d_qp_status, (size_t)max_batch * sizeof(int)));
     CKC(cudaMalloc(&s->d_ctl_d, (size_t)NCTL_D * s->chunk * sizeof(double)));
     CKC(cudaMalloc(&s->d_ctl_i, (size_t)NCTL_I * s->chunk * sizeof(int)));
@@ -607,6 +713,84 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
     return 0;
 }
 
+
+// ---- group path: one persistent launch per chunk ------------------------------------------------
+template <class M, int G, int MINB>
+static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
+                        const GrpOut& out, cudaStream_t st)
+{
+    using GP = Grp<M, G>;
+    const size_t smem = (size_t)GRP_WARPS * GP::WARP_D * sizeof(double);
+    static int blocks_per_sm = 0;          // per template instantiation
+    if (!blocks_per_sm) {
+        CK(cudaFuncSetAttribute(k_ipm_group<M, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ipm_group<M, G, MINB>, GRP_WARPS * 32, smem));
+        if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_group does not fit on an SM");
+        if (const char* e = getenv("NMPC_GRP_BPS")) { int v = atoi(e); if (v >= 1 && v < nb) nb = v; }
+        blocks_per_sm = nb;
+    }
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
+    const int per_block = GRP_WARPS * GP::NSLOT;
+    int blocks = nsm * blocks_per_sm;
+    const int need = (n + per_block - 1) / per_block;
+    if (blocks > need) blocks = need;
+    s->grp_blocks = blocks;
+    CK(cudaMemsetAsync(s->d_cnt, 0, sizeof(int), st));
+    k_ipm_group<M, G, MINB><<<blocks, GRP_WARPS * 32, smem, st>>>(i0, n, tb, d_We, ldWe, o, s->d_ws, s->d_cnt, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class M>
+static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
+                              double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st)
+{
+    using S = Rti<M>;
+    using GR = GRec<S::NV>;
+    const Tables tb = make_tables(s);
+    const IpmOpts o = to_core_opts(s->opts);
+    const int nchunks = (B + s->chunk - 1) / s->chunk;
+    int rc = ensure_events(s, nchunks);
+    if (rc) return rc;
+    s->last_chunks = nchunks; s->last_launches = 0;
+    k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
+    s->last_launches++;
+    const size_t sm_lin = (size_t)LIN_BLOCK * (GR::LHD | 1) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_linearize_g<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lin));
+        attr_set = true;
+    }
+    const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * s->chunk;
+        const int n = (B - i0) < s->chunk ? (B - i0) : s->chunk;
+        cudaEvent_t* ev = &s->ev[(size_t)c * 4];
+        CK(cudaEventRecord(ev[0], st));
+        dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
+        k_linearize_g<M><<<g1, LIN_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
+        CK(cudaEventRecord(ev[1], st));
+        const int G = s->grp_G;
+        if constexpr (S::NV == 2) {
+            if (G == 8) rc = launch_group<M, 8, 3>(s, i0, n, tb, d_We, B, o, out, st);
+            else if (G == 16) rc = launch_group<M, 16, 3>(s, i0, n, tb, d_We, B, o, out, st);
+            else rc = launch_group<M, 32, 3>(s, i0, n, tb, d_We, B, o, out, st);
+        } else {
+            if (G == 32) rc = launch_group<M, 32, 2>(s, i0, n, tb, d_We, B, o, out, st);
+            else rc = launch_group<M, 16, 2>(s, i0, n, tb, d_We, B, o, out, st);
+        }
+        if (rc) return rc;
+        CK(cudaEventRecord(ev[2], st));
+        k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
+        CK(cudaEventRecord(ev[3], st));
+        s->last_launches += 3;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref,
                                      const double* d_We, double* d_x, double* d_u, int ldxu,
                                      int* d_status, int* d_qp_iter, double* d_stats, void* stream)
@@ -624,7 +808,13 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
     if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
     if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
     CK(cudaEventRecord(s->ev_total[0], st));
-    switch (s->model) {
+    if (s->k3_group) {
+        switch (s->model) {
+            case 0: rc = solve_device_group<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+            case 1: rc = solve_device_group<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+            default: rc = solve_device_group<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
+        }
+    } else switch (s->model) {
         case 0: rc = solve_device_t<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
         case 1: rc = solve_device_t<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
         default: rc = solve_device_t<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;

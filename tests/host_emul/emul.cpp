@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "../../nmpc_nav_control_b200/csrc/rti_core.cuh"
+#include "../../nmpc_nav_control_b200/csrc/rti_group.cuh"
 
 using namespace nmpc;
 
@@ -58,5 +59,77 @@ extern "C" int emul_rti(int model, int B, const double* W, const double* We, con
         case 1: return run<Omni4Model>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
         case 2: return run<TricModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
     }
+    return -1;
+}
+
+// ---- the lane-group K3 (rti_group.cuh): one emulated warp of 32 lanes, phases run lane by lane ----
+template <class M, int G>
+static int run_group(int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                     const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                     const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                     double* x, double* u, int* status, int* iters, double* stats)
+{
+    using S = Rti<M>;
+    using GP = Grp<M, G>;
+    using GR = typename GP::R;
+    constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
+    std::vector<double> lti(NSTAGE * 4 * NV);
+    for (int k = 0; k < NSTAGE; k++) {
+        double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
+        S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+    }
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt};
+    std::vector<double> ws((size_t)B * GR::inst_doubles, 0.0);
+    std::vector<double> WeT;                  // kernel layout of the per-instance terminal weights: [nx][B]
+    if (We_inst) { WeT.resize((size_t)NX * B); for (int i = 0; i < B; i++) for (int j = 0; j < NX; j++) WeT[(size_t)j * B + i] = We_inst[(size_t)i * NX + j]; }
+    for (int i = 0; i < B; i++) {
+        double* xi = x + (size_t)i * (NSTAGE + 1) * NX;
+        double* ui = u + (size_t)i * NSTAGE * NU;
+        const double* yi = yref + (size_t)i * (NSTAGE + 1) * nyref;
+        const double* wei = We_inst ? We_inst + (size_t)i * NX : We;
+        for (int k = 0; k <= NSTAGE; k++) {
+            double* rec = GP::rec_of(ws.data(), i, k);
+            S::template linearize_stage<GR, 1>(k, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU, xi + (k < NSTAGE ? k + 1 : k) * NX,
+                                               yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei, rec, rec);
+        }
+    }
+    std::vector<int> qs(B, -1), qi(B, 0);
+    std::vector<double> st((size_t)8 * B, 0.0);
+    GrpOut out{qs.data(), qi.data(), st.data(), B};
+    int next = 0;
+    const int nwarps = 2;                     // the second warp finds the queue empty unless B is large
+    for (int wp = 0; wp < nwarps; wp++) {
+        std::vector<typename GP::Lane> lanes(32);
+        std::vector<double> sm(GP::WARP_D, 0.0);
+        for (int l = 0; l < 32; l++) GP::init_lane(lanes[l], l);
+        GP::run_warp(lanes.data(), sm.data(), ws.data(), 0, B, &next, tb, We_inst ? WeT.data() : nullptr, B, *o, out);
+    }
+    for (int i = 0; i < B; i++) {
+        status[i] = qs[i]; iters[i] = qi[i];
+        if (stats) for (int q = 0; q < 7; q++) stats[i * 8 + q] = st[(size_t)q * B + i];
+        double* xi = x + (size_t)i * (NSTAGE + 1) * NX;
+        double* ui = u + (size_t)i * NSTAGE * NU;
+        if (qs[i] == 0 || qs[i] == 1)
+            for (int k = 0; k <= NSTAGE; k++)
+                S::template step_stage<GR, 1>(k, GP::rec_of(ws.data(), i, k), x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
+    }
+    return 0;
+}
+
+extern "C" int emul_rti_group(int model, int G, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                              const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                              const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                              double* x, double* u, int* status, int* iters, double* stats)
+{
+#define RG(MODEL, GG) return run_group<MODEL, GG>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats)
+    if (model == 0 && G == 8) RG(DiffModel, 8);
+    if (model == 0 && G == 16) RG(DiffModel, 16);
+    if (model == 0 && G == 32) RG(DiffModel, 32);
+    if (model == 1 && G == 16) RG(Omni4Model, 16);
+    if (model == 1 && G == 32) RG(Omni4Model, 32);
+    if (model == 2 && G == 8) RG(TricModel, 8);
+    if (model == 2 && G == 16) RG(TricModel, 16);
+    if (model == 2 && G == 32) RG(TricModel, 32);
+#undef RG
     return -1;
 }
