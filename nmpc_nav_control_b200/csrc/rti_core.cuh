@@ -119,6 +119,7 @@ struct Tables {
     const double* p;      // [N][NP]
     const double* lti;    // [N][4*NV] av, ar, au, ru per channel (written by the LTI set-up kernel)
     double dt;
+    const double* lte;    // [N][4*NV+2] the same followed by the constants 0 and 1 (group path: table-driven lane roles)
 };
 
 template <int NV>
@@ -277,6 +278,49 @@ struct Rti {
 #pragma unroll
             for (int j = 0; j < NX; j++) it[(RR::Z + NU + j) * LS] = x0bar[j] - xk[j];
         }
+    }
+
+    // ------------------------------------------------------------------------------------
+    // Cold start of the interior point for one (instance, stage) (HPIPM INIT_VAR with
+    // warm_start = 0; the `first` branch of stage_B_update), written straight into the record so
+    // that the group path's first factorising sweep is an ordinary one with step length 0:
+    // z = 0 (bounded components projected thr0 inside their bounds; the stage-0 state stays the
+    // constant written by linearize_stage), pi = 0, slacks from the bounds, lam = mu0 / t, and
+    // zero step / second-order terms.   lin: DLB, DUB of the stage;  it: T, LAM, Z, PI, DZ, MC.
+    // ------------------------------------------------------------------------------------
+    template <class RR, int LS>
+    NMPC_HD static void coldstart_stage(int k, const IpmOpts& o, const double* lin, double* it)
+    {
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+#pragma unroll
+        for (int c = 0; c < NU; c++) it[(RR::Z + c) * LS] = 0.0;
+        if (hasX) {
+#pragma unroll
+            for (int j = 0; j < NX; j++) it[(RR::Z + NU + j) * LS] = 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < NB2; b++) {
+            const bool act = (b < NV) ? hasU : hasX;
+            const double dl = lin[(RR::DLB + b) * LS], du_ = lin[(RR::DUB + b) * LS];
+            double zb = 0.0, t_l = -dl, t_u = du_;
+            if (t_l < o.thr0) {
+                if (t_u < o.thr0) { zb = 0.5 * (dl + du_); t_l = o.thr0; t_u = o.thr0; }
+                else { t_l = o.thr0; zb = dl + o.thr0; }
+            } else if (t_u < o.thr0) { t_u = o.thr0; zb = du_ - o.thr0; }
+            if (act) {
+                it[(RR::Z + (b < NV ? b : NU + 3 + b)) * LS] = zb;
+                it[(RR::T + b) * LS] = t_l; it[(RR::T + NB2 + b) * LS] = t_u;
+                it[(RR::LAM + b) * LS] = o.mu0 / t_l; it[(RR::LAM + NB2 + b) * LS] = o.mu0 / t_u;
+            } else {
+                it[(RR::T + b) * LS] = 1.0; it[(RR::T + NB2 + b) * LS] = 1.0;
+                it[(RR::LAM + b) * LS] = 0.0; it[(RR::LAM + NB2 + b) * LS] = 0.0;
+            }
+            it[(RR::MC + b) * LS] = 0.0; it[(RR::MC + NB2 + b) * LS] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NX; j++) it[(RR::PI + j) * LS] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NZ; c++) it[(RR::DZ + c) * LS] = 0.0;
     }
 
     // ------------------------------------------------------------------------------------

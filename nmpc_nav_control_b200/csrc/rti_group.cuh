@@ -130,60 +130,47 @@ struct Grp {
     using LaneCtl = typename S::LaneCtl;
     static constexpr int G = G_, NSLOT = 32 / G;
     static constexpr int NV = S::NV, NX = S::NX, NU = S::NU, NZ = S::NZ, NY = S::NY, NC = S::NC, NB2 = S::NB2, NLU = S::NLU;
-    static constexpr int CW = (NZ + G - 1) / G;          // z components per lane
+    static constexpr int NCT = 2 * NB2;                  // one-sided constraints per stage
     static constexpr int NK = NSTAGE + 1;
-    static constexpr int WL = G > NX ? NX : 0;           // lane that writes the per-stage scalars of the factorisation
-    static_assert(G >= NX && 32 % G == 0, "one state column per lane");
+    static constexpr int LTE = 4 * NV + 2, LT_ZERO = 4 * NV, LT_ONE = 4 * NV + 1;
+    // lane roles (all table driven, see init_lane):
+    //   constraint role : lane c < NCT owns one-sided constraint c (lower NB2, then upper NB2)
+    //   component role  : lane q < NC owns the z component whose column of the pose rows E is q
+    //                     (theta | actual | ref | u); lanes NC.. own the pose components x, y (unit columns)
+    //   column/row role : lane j < NX owns state column j of the cost-to-go, of M and K, and row j of
+    //                     the dynamics;  lanes UL0.. own the control columns
+    static constexpr int XYL = NC;                        // first lane of the x / y components
+    static constexpr int XY_PER = (G - NC >= 2) ? 1 : 2;  // x and y on two lanes, or both on lane NC
+    static constexpr int ULN = (G - NX >= NV) ? NV : 1;   // lanes that own control columns (NV / ULN each) ...
+    static constexpr int ULB = G > NX ? NX : 0;           // ... starting at this lane
+    static constexpr int WL = G > NX ? NX : 0;            // lane that writes the per-stage scalars of the factorisation
+    static_assert(G >= NX && G >= NCT && G > NC && 32 % G == 0, "one state column, one constraint, one component per lane");
     using R = GRec<NV>;
 
     // ---- shared-memory scratch of one slot (doubles) ----------------------------------------
     static constexpr int O_IN = 0;                        // [2][NREC] double-buffered record image
     static constexpr int O_CAR = O_IN + 2 * R::NREC;      // [2][3][NX] carries of the B sweep: pio, dpi, xn
                                                           //   (F: dx [2][NX]; Bd: dp [2][NX])
-    static constexpr int O_ZB = O_CAR + 6 * NX;           // NZ   new z of the stage, z order
-    static constexpr int O_RB = O_ZB + NZ;                // NX   dynamics residual
-    static constexpr int O_PV = O_RB + NX;                // NX   gradient of the cost-to-go
-    static constexpr int O_PBA = O_PV + NX;               // [NX][NZ]  P * [A B], columns in w order [x; u]
+    static constexpr int O_PV = O_CAR + 6 * NX;           // NX   gradient of the cost-to-go
+    static constexpr int O_RB = O_PV + NX;                // NX   dynamics residual
+    static constexpr int O_GX = O_RB + NX;                // NX   stage gradient, state rows
+    static constexpr int O_DGX = O_GX + NX;               // NX   diagonal H + reg + Gamma, state rows
+    static constexpr int O_GU = O_DGX + NX;               // NV   control gradient / F: s_a / Bd: q_u
+    static constexpr int O_DGU = O_GU + NV;               // NV
+    static constexpr int O_CB = O_DGU + NV;               // [NCT+1][4] per-constraint terms (last entry: zeros)
+    static constexpr int O_PBA = O_CB + 4 * (NCT + 1);    // [NX][NZ]  P * [A B], columns [x; u]
     static constexpr int O_MUU = O_PBA + NX * NZ;         // [NV][NV]
-    static constexpr int O_GU = O_MUU + NV * NV;          // NV   control gradient / F: s_a / Bd: q_u
-    static constexpr int O_KB = O_GU + NV;                // [NV][NX]
+    static constexpr int O_KB = O_MUU + NV * NV;          // [NV][NX]
+    static constexpr int O_DUMP = O_KB + NV * NX;         // 4    target of role-masked stores
     static constexpr int O_RED = O_IN;                    // [G][8] reductions at the end of a sweep / queue hand-out (the record image is dead there)
-    static constexpr int O_END = O_KB + NV * NX;
+    static constexpr int O_END = O_DUMP + 4;
     static_assert(G * 8 <= 2 * R::NREC, "reduction buffer must fit into the record image");
     // slot stride: even (16-byte copies) and = 8 mod 16 so that equal offsets of neighbouring slots
     // fall into different bank groups
     static constexpr int SLOT_D = ((O_END + 15) / 16) * 16 + 8;
     static constexpr int WARP_D = SLOT_D * NSLOT;         // doubles of shared memory per warp
 
-    // z-order index of w-order component (w order = [x; u], the order lanes own components in)
-    NMPC_HD static constexpr int zc(int w) { return w < NX ? NU + w : w - NX; }
-    // bound pair of w-order component: u_a -> a, ref state j >= 3+NV -> j-3, else -1
-    NMPC_HD static constexpr int bnd(int w) { return w >= NX ? w - NX : (w >= 3 + NV ? w - 3 : -1); }
-
-    // 1.0 / 0.0 indicator: selecting a register-array element by a lane-dependent index with
-    // arithmetic keeps the array in registers (a select chain is turned into a local-memory index)
-    NMPC_HD static double sel(bool b) { return b ? 1.0 : 0.0; }
-
-    // (column w of J = [A B]) . v, v indexed by state (stride 1); E = pose rows [3][NC], lt = av|ar|au|ru
-    NMPC_HD static double jcol_dot(int w, const double* v, const double* E, const double* lt)
-    {
-        if (w < NX) {
-            const int j = w;
-            if (j < 2) return v[j];
-            if (j == 2) return E[0] * v[0] + E[NC] * v[1] + E[2 * NC] * v[2];
-            if (j < 3 + NV) {
-                const int c = j - 3;
-                return E[1 + c] * v[0] + E[NC + 1 + c] * v[1] + E[2 * NC + 1 + c] * v[2] + grp_ldg(lt + c) * v[3 + c];
-            }
-            const int c = j - 3 - NV;
-            return E[1 + NV + c] * v[0] + E[NC + 1 + NV + c] * v[1] + E[2 * NC + 1 + NV + c] * v[2] + grp_ldg(lt + NV + c) * v[3 + c] +
-                   v[3 + NV + c];
-        }
-        const int a = w - NX, cu = 1 + 2 * NV + a;
-        return E[cu] * v[0] + E[NC + cu] * v[1] + E[2 * NC + cu] * v[2] + grp_ldg(lt + 2 * NV + a) * v[3 + a] +
-               grp_ldg(lt + 3 * NV + a) * v[3 + NV + a];
-    }
-    // same with everything in registers (static indices after unrolling)
+    // static-index products with J = [A B] (registers only): (column w of J) . v, w in [x; u] order
     NMPC_HD static double jcol_dot_r(int w, const double* v, const double* E, const double* lt)
     {
         if (w < NX) {
@@ -200,66 +187,90 @@ struct Grp {
         const int a = w - NX, cu = 1 + 2 * NV + a;
         return E[cu] * v[0] + E[NC + cu] * v[1] + E[2 * NC + cu] * v[2] + lt[2 * NV + a] * v[3 + a] + lt[3 * NV + a] * v[3 + NV + a];
     }
-    // (row i of J) . [zu; zx]
-    NMPC_HD static double jrow_dot(int i, const double* zu, const double* zx, const double* E, const double* lt)
-    {
-        if (i < 3) {
-            double s = (i < 2 ? zx[i] : 0.0) + E[i * NC] * zx[2];
-#pragma unroll
-            for (int c = 0; c < NV; c++)
-                s += E[i * NC + 1 + c] * zx[3 + c] + E[i * NC + 1 + NV + c] * zx[3 + NV + c] + E[i * NC + 1 + 2 * NV + c] * zu[c];
-            return s;
-        }
-        const int c = i < 3 + NV ? i - 3 : i - 3 - NV;
-        double uc = 0.0;        // zu may live in registers: select, do not index dynamically
-#pragma unroll
-        for (int a = 0; a < NV; a++) uc += zu[a] * sel(a == c);
-        if (i < 3 + NV) return grp_ldg(lt + c) * zx[3 + c] + grp_ldg(lt + NV + c) * zx[3 + NV + c] + grp_ldg(lt + 2 * NV + c) * uc;
-        return zx[3 + NV + c] + grp_ldg(lt + 3 * NV + c) * uc;
-    }
+    // 1.0 / 0.0 indicator: selecting a register-array element by a lane-dependent index with
+    // arithmetic keeps the array in registers (a select chain is turned into a local-memory index)
+    NMPC_HD static double sel(bool b) { return b ? 1.0 : 0.0; }
 
     // ---- state of one lane (registers on the device) ----------------------------------------
     struct Lane {
-        int r, slot;              // role in the group, slot of the warp
+        int r, slot;              // role index in the group, slot of the warp
         int li;                   // instance (index into the chunk) of the slot, -1 = none
-        bool act, first, run;     // slot has an instance / its next B sweep is the cold start / takes part in the current sweep
+        bool act, first, run;     // slot has an instance / its next B sweep is the first / takes part in the current sweep
         LaneCtl c;                // replicated over the lanes of the slot
         double astep;             // damped step applied by the running B sweep
-        double We;                // terminal weight of this lane's state component
+        const double* We;         // terminal weights of the instance: We[j * ldWe]
+        int ldWe;
+        // component role (generic components q = r < NC)
+        int cq_z, cq_x, cq_y;     // z-order index; state index (-1: control); index into W / y
+        int cq_bl, cq_bu;         // lower / upper constraint (NCT: none)
+        int cq_i1, cq_i2, cq_k1, cq_k2;   // LTI part of the column of J: k1 * v[i1] + k2 * v[i2], k from the lte table
+        // constraint role (c = r < NCT)
+        int ct_z, ct_x, ct_u;     // z-order index of the bounded component; its state index or -1; its control index or -1
+        double ct_s;              // +1 lower, -1 upper
         // B sweep
         double Pc[NX];            // column r of the cost-to-go of the successor stage
-        double g[CW], Gam[CW], H[CW];
         double Ef[3 * NC];        // pose rows of [A|B] of the stage
         double lt[4 * NV];
-        double Mx[NZ];            // column r of M = J'PJ + D, rows in w order
+        double Mx[NZ];            // column r of M = J'PJ + D, rows [x; u]
         double Kc[NV];            // column r of K
         double lh[NV];
+        double gx;                // stage gradient of state r
         double ng, nb, nd, nm, musum, lru;
         // F / Bd sweeps
-        double dxr;               // dx (F) / dp (Bd) component r
+        double dxr;               // dx (F) / q_x (Bd) component r
         double du[NV];
         double alpha, S0, S1, S2;
     };
+
+    NMPC_HD static void init_lane(Lane& L, int lane)
+    {
+        const int r = lane % G;
+        L.r = r; L.slot = lane / G; L.li = -1;
+        L.act = false; L.first = false; L.run = false;
+        L.c.init(false);
+        L.astep = 0.0; L.We = nullptr; L.ldWe = 0;
+        // component role: E column q = r -> theta | actual c | ref c | u a
+        L.cq_z = 0; L.cq_x = -1; L.cq_y = 0; L.cq_bl = NCT; L.cq_bu = NCT;
+        L.cq_i1 = 0; L.cq_i2 = 0; L.cq_k1 = LT_ZERO; L.cq_k2 = LT_ZERO;
+        if (r == 0) { L.cq_x = 2; }
+        else if (r <= NV) { const int c = r - 1; L.cq_x = 3 + c; L.cq_i1 = 3 + c; L.cq_k1 = c; }
+        else if (r <= 2 * NV) {
+            const int c = r - 1 - NV;
+            L.cq_x = 3 + NV + c; L.cq_i1 = 3 + c; L.cq_k1 = NV + c; L.cq_i2 = 3 + NV + c; L.cq_k2 = LT_ONE;
+            L.cq_bl = NV + c; L.cq_bu = NB2 + NV + c;
+        } else if (r < NC) {
+            const int a = r - 1 - 2 * NV;
+            L.cq_i1 = 3 + a; L.cq_k1 = 2 * NV + a; L.cq_i2 = 3 + NV + a; L.cq_k2 = 3 * NV + a;
+            L.cq_bl = a; L.cq_bu = NB2 + a;
+            L.cq_z = a; L.cq_y = NX + a;
+        }
+        if (L.cq_x >= 0) { L.cq_z = NU + L.cq_x; L.cq_y = L.cq_x; }
+        // constraint role
+        const int b = r % NB2;
+        L.ct_s = (r < NB2) ? 1.0 : -1.0;
+        L.ct_u = b < NV ? b : -1;
+        L.ct_x = b < NV ? -1 : 3 + b;
+        L.ct_z = b < NV ? b : NU + 3 + b;
+    }
 
     NMPC_HD static double* rec_of(double* ws, int li, int k) { return ws + (size_t)li * R::inst_doubles + (size_t)k * R::NREC; }
 
     // copy doubles [d0, d1) of the record (16-byte chunks spread over the group)
     NMPC_HD static void copy_range(double* dst, const double* src, int d0, int d1, int r)
     {
-        for (int c = d0 + 2 * r; c < d1; c += 2 * G) grp_cp16(dst + c, src + c);
+#pragma unroll
+        for (int c = d0; c < d1; c += 2 * G)
+            if (c + 2 * r < d1) grp_cp16(dst + c + 2 * r, src + c + 2 * r);
     }
 
     enum { SW_B = 0, SW_F = 1, SW_BD = 2, SW_FD = 3 };
 
     template <int KIND>
-    NMPC_HD static void issue(const Lane& L, double* ws, double* scr, int k, int buf)
+    NMPC_HD static void issue(const Lane& L, const double* src, double* dst)
     {
-        if (!L.run) return;
-        double* dst = scr + O_IN + buf * R::NREC;
-        const double* src = rec_of(ws, L.li, k);
         if (KIND == SW_B) {
             copy_range(dst, src, R::Q, R::LHD, L.r);
-            if (!L.first) copy_range(dst, src, R::MC, R::NREC, L.r);
+            copy_range(dst, src, R::MC, R::NREC, L.r);
         } else if (KIND == SW_F) {
             copy_range(dst, src, R::DLB, R::DZA, L.r);
             copy_range(dst, src, R::T, R::PI, L.r);
@@ -294,9 +305,33 @@ struct Grp {
         GRP_PHASE_END
     }
 
+    // J' v for the lane's generic component (E column q = r): v in shared memory, indexed by state
+    NMPC_HD static double jt_comp(const Lane& L, double e0, double e1, double e2, double k1, double k2, const double* v)
+    {
+        return e0 * v[0] + e1 * v[1] + e2 * v[2] + k1 * v[L.cq_i1] + k2 * v[L.cq_i2];
+    }
+    // (row i of J) . [zu; zx] with the vectors given as functors (shared memory or registers)
+    template <class FU, class FX>
+    NMPC_HD static double jrow(int i, FU zu, FX zx, const double* E, const double* lt)
+    {
+        if (i < 3) {
+            double s0 = (i < 2 ? zx(i) : 0.0) + E[i * NC] * zx(2), s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                s0 += E[i * NC + 1 + c] * zx(3 + c) + E[i * NC + 1 + 2 * NV + c] * zu(c);
+                s1 += E[i * NC + 1 + NV + c] * zx(3 + NV + c);
+            }
+            return s0 + s1;
+        }
+        const int c = i < 3 + NV ? i - 3 : i - 3 - NV;
+        if (i < 3 + NV) return grp_ldg(lt + c) * zx(3 + c) + grp_ldg(lt + NV + c) * zx(3 + NV + c) + grp_ldg(lt + 2 * NV + c) * zu(c);
+        return zx(3 + NV + c) + grp_ldg(lt + 3 * NV + c) * zu(c);
+    }
+
     // =========================================================================================
-    // B sweep: (apply the previous step) + residuals + Riccati factorisation, stages N..0
-    // (same arithmetic as Rti::stage_B_update / stage_B_riccati, one component per lane)
+    // B sweep: apply the previous step, residuals, Riccati factorisation, stages N..0
+    // (the arithmetic of Rti::stage_B_update / stage_B_riccati; the cold start is an ordinary
+    // sweep with step 0 over the records initialised by Rti::coldstart_stage)
     // =========================================================================================
     NMPC_HD static void sweep_B(Lane* lanes, double* sm, double* ws, const Tables& tb, const IpmOpts& o)
     {
@@ -305,7 +340,8 @@ struct Grp {
             if (L.run) {
                 double* scr = sm + L.slot * SLOT_D;
                 if (L.r < NX) { scr[O_CAR + L.r] = 0.0; scr[O_CAR + NX + L.r] = 0.0; scr[O_CAR + 2 * NX + L.r] = 0.0; scr[O_PV + L.r] = 0.0; }
-                issue<SW_B>(L, ws, scr, NSTAGE, 0);
+                if (L.r < 4) scr[O_CB + 4 * NCT + L.r] = 0.0;
+                issue<SW_B>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
             grp_cp_commit();
         GRP_PHASE_END
@@ -313,111 +349,136 @@ struct Grp {
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lti + (hasU ? k : 0) * 4 * NV;
+            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
-            // ---- B1: prefetch the next stage; per component: step, residuals, barrier terms ----
+            // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.slot * SLOT_D;
-                if (s < NSTAGE) issue<SW_B>(L, ws, scr, k - 1, buf ^ 1);
+                double* grec = rec_of(ws, L.li, k);
+                if (s < NSTAGE) issue<SW_B>(L, grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 const double* rec = scr + O_IN + buf * R::NREC;
+                const double a_step = L.astep;
+                if (L.r < NCT) {
+                    const int c = L.r;
+                    const bool actc = (L.ct_u >= 0) ? hasU : hasX;
+                    double rpart = 0.0, lpart = 0.0, gpart = 0.0, Gp = 0.0;
+                    if (actc) {
+                        const double sg = L.ct_s;
+                        const double dbd = rec[R::DLB + c], z = rec[R::Z + L.ct_z], dz = rec[R::DZ + L.ct_z];
+                        const double lam = rec[R::LAM + c], t = rec[R::T + c], mc = rec[R::MC + c];
+                        const double rd = sg * (dbd - z) + t;
+                        const double rm = lam * t - o.tau_min + L.c.mcw * mc - L.c.sigmu;
+                        const double dt = sg * dz - rd;
+                        const double dlam = -(lam * dt + rm) / t;
+                        const double lam_n = lam + a_step * dlam, t_n = t + a_step * dt, zn = z + a_step * dz;
+                        rpart = -sg * (lam + dlam);
+                        const double rd_n = sg * (dbd - zn) + t_n;
+                        const double pm = lam_n * t_n;
+                        L.musum += pm;
+                        const double rm_n = pm - o.tau_min;
+                        L.nd = fmax(L.nd, fabs(rd_n));
+                        L.nm = fmax(L.nm, fabs(rm_n));
+                        const double ti = t_n < o.t_min ? 1.0 / o.t_min : 1.0 / t_n;
+                        const double lc = lam_n < o.lam_min ? o.lam_min : lam_n;
+                        Gp = ti * lc;
+                        lpart = -sg * lam_n;
+                        gpart = sg * (ti * (rm_n - lam_n * rd_n));
+                        grec[R::LAM + c] = lam_n; grec[R::T + c] = t_n;
+                    }
+                    scr[O_CB + 4 * c] = rpart; scr[O_CB + 4 * c + 1] = lpart; scr[O_CB + 4 * c + 2] = gpart; scr[O_CB + 4 * c + 3] = Gp;
+                }
+                if (hasU) {
+#pragma unroll
+                    for (int i = 0; i < 3 * NC; i++) L.Ef[i] = rec[R::E + i];
+#pragma unroll
+                    for (int i = 0; i < 4 * NV; i++) L.lt[i] = grp_ldg(ltk + i);
+                    if (L.r < NX) {
+#pragma unroll
+                        for (int w = 0; w < NZ; w++)
+                            if (hasX || w >= NX) scr[O_PBA + L.r * NZ + w] = jcol_dot_r(w, L.Pc, L.Ef, L.lt);
+                    }
+                }
+            GRP_PHASE_END
+            // ---- B1b: one component per lane: step, stationarity residual, multiplier step; row r of
+            //      the dynamics residual --------------------------------------------------------------
+            GRP_PHASE_BEGIN(lanes)
+                if (!L.run) continue;
+                double* scr = sm + L.slot * SLOT_D;
                 double* grec = rec_of(ws, L.li, k);
+                const double* rec = scr + O_IN + buf * R::NREC;
                 const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
                 double* carn = scr + O_CAR + ((s & 1) ^ 1) * 3 * NX;
-                const double a_step = L.astep, sigmu = L.c.sigmu, mcw = L.c.mcw;
-                const bool first = L.first;
-#pragma unroll
-                for (int t = 0; t < CW; t++) {
-                    const int w = L.r + t * G;
-                    if (w >= NZ) continue;
-                    const bool isx = w < NX;
-                    const int c = zc(w), b = bnd(w);
+                const double a_step = L.astep;
+                if (L.r < NC) {
+                    // generic component: column q = r of the pose rows E
+                    const int q = L.r;
+                    const bool isx = L.cq_x >= 0;
                     const bool has = isx ? hasX : hasU;
-                    const double H = hasU ? tb.dt * grp_ldg(tb.W + k * NY + w)   /* w order = y order [x; u] */ : (isx ? L.We : 0.0);
-                    const double q = rec[R::Q + c];
-                    double v1 = 0.0, v2 = 0.0;
-                    if (hasU) { v1 = jcol_dot(w, car, rec + R::E, ltk); v2 = jcol_dot(w, car + NX, rec + R::E, ltk); }
-                    double z, pin = 0.0, pi_old = 0.0, dpi_new = 0.0;
-                    double ll = 0.0, lu = 0.0, tl = 1.0, tu = 1.0, dl = 0.0, du_ = 0.0;
-                    const bool act = b >= 0 && has;
-                    if (b >= 0) { dl = rec[R::DLB + b]; du_ = rec[R::DUB + b]; }
-                    if (first) {
-                        // cold start (HPIPM INIT_VAR with warm_start = 0)
-                        z = (isx && !hasX) ? grec[R::Z + c] : 0.0;
-                        if (b >= 0) {
-                            double zb = 0.0, t_l = -dl, t_u = du_;
-                            if (t_l < o.thr0) {
-                                if (t_u < o.thr0) { zb = 0.5 * (dl + du_); t_l = o.thr0; t_u = o.thr0; }
-                                else { t_l = o.thr0; zb = dl + o.thr0; }
-                            } else if (t_u < o.thr0) { t_u = o.thr0; zb = du_ - o.thr0; }
-                            if (act) { z = zb; tl = t_l; tu = t_u; ll = o.mu0 / t_l; lu = o.mu0 / t_u; }
-                        }
-                    } else {
-                        z = rec[R::Z + c];
-                        const double dz = has ? rec[R::DZ + c] : 0.0;
-                        if (isx && hasX) { pin = rec[R::PI + w]; pi_old = pin; }
-                        double ldo = 0.0, dld = 0.0;
-                        if (act) {
-                            ll = rec[R::LAM + b]; lu = rec[R::LAM + NB2 + b];
-                            tl = rec[R::T + b];   tu = rec[R::T + NB2 + b];
-                            const double mc_l = rec[R::MC + b], mc_u = rec[R::MC + NB2 + b];
-                            const double rd_l = dl - z + tl, rd_u = -du_ + z + tu;
-                            const double rm_l = ll * tl - o.tau_min + mcw * mc_l - sigmu;
-                            const double rm_u = lu * tu - o.tau_min + mcw * mc_u - sigmu;
-                            const double dt_l = dz - rd_l, dt_u = -dz - rd_u;
-                            const double dl_l = -(ll * dt_l + rm_l) / tl;
-                            const double dl_u = -(lu * dt_u + rm_u) / tu;
-                            ldo = lu - ll;
-                            dld = dl_l - dl_u;
-                            ll += a_step * dl_l; lu += a_step * dl_u;
-                            tl += a_step * dt_l; tu += a_step * dt_u;
-                        }
-                        if (!isx) {
-                            if (hasU) {
-                                const double r = q + H * z + ldo + v1 + H * dz - dld + v2;
-                                L.lru = fmax(L.lru, fabs(r));
-                            }
-                        } else if (hasX) {
-                            // adjoint recursion for the multiplier step of the dynamics that define x_k
-                            double r = q + H * z - pin + v1 + H * dz + v2;
-                            if (b >= 0) r += ldo - dld;
-                            dpi_new = r;
-                            pin += a_step * r;
-                        }
-                        z += a_step * dz;
-                    }
-                    // residuals at the (new) iterate
-                    double g = q + H * z + (lu - ll) + (v1 + a_step * v2);
-                    if (isx) g -= pin;
+                    const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
+                    const double k1 = grp_ldg(ltk + L.cq_k1), k2 = grp_ldg(ltk + L.cq_k2);
+                    const double v1 = jt_comp(L, e0, e1, e2, k1, k2, car);
+                    const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
+                    const double v3 = jt_comp(L, e0, e1, e2, k1, k2, scr + O_PV);
+                    const double H = hasU ? tb.dt * grp_ldg(tb.W + k * NY + L.cq_y) : (isx ? L.We[(size_t)L.cq_x * L.ldWe] : 0.0);
+                    const double qv = rec[R::Q + L.cq_z], z = rec[R::Z + L.cq_z], dz = rec[R::DZ + L.cq_z];
+                    const bool haspi = isx && hasX;
+                    const double pin = haspi ? rec[R::PI + (isx ? L.cq_x : 0)] : 0.0;
+                    const double* cl = scr + O_CB + 4 * L.cq_bl;
+                    const double* cu = scr + O_CB + 4 * L.cq_bu;
+                    double r = qv + H * z - pin + v1 + H * dz + v2;
+                    r += cl[0] + cu[0];
+                    const double pin_n = haspi ? pin + a_step * r : 0.0;
+                    const double zn = z + a_step * dz;
+                    double g = qv + H * zn - pin_n + (v1 + a_step * v2);
+                    g += cl[1] + cu[1];
                     if (has) L.ng = fmax(L.ng, fabs(g));
-                    double Gam = 0.0;
-                    if (act) {
-                        const double rd_l = dl - z + tl, rd_u = -du_ + z + tu;
-                        const double pm_l = ll * tl, pm_u = lu * tu;
-                        L.musum += pm_l + pm_u;
-                        const double rm_l = pm_l - o.tau_min, rm_u = pm_u - o.tau_min;
-                        L.nd = fmax(L.nd, fmax(fabs(rd_l), fabs(rd_u)));
-                        L.nm = fmax(L.nm, fmax(fabs(rm_l), fabs(rm_u)));
-                        const double ti_l = tl < o.t_min ? 1.0 / o.t_min : 1.0 / tl;
-                        const double ti_u = tu < o.t_min ? 1.0 / o.t_min : 1.0 / tu;
-                        const double l_l = ll < o.lam_min ? o.lam_min : ll;
-                        const double l_u = lu < o.lam_min ? o.lam_min : lu;
-                        Gam = ti_l * l_l + ti_u * l_u;
-                        g += ti_l * (rm_l - ll * rd_l) - ti_u * (rm_u - lu * rd_u);
+                    if (!isx && hasU) L.lru = fmax(L.lru, fabs(r));
+                    g += cl[2] + cu[2];
+                    g += v3;
+                    const double dg = H + o.reg_prim + (cl[3] + cu[3]);
+                    grec[R::Z + L.cq_z] = zn;
+                    if (isx) {
+                        const int j = L.cq_x;
+                        grec[R::PI + j] = pin_n;
+                        carn[j] = pin; carn[NX + j] = haspi ? r : 0.0; carn[2 * NX + j] = zn;
+                        scr[O_GX + j] = g; scr[O_DGX + j] = dg;
+                    } else {
+                        scr[O_GU + L.cq_z] = g; scr[O_DGU + L.cq_z] = dg;
                     }
-                    L.g[t] = g; L.Gam[t] = Gam; L.H[t] = H;
-                    // store the iterate, hand the carries to stage k-1
-                    if (!isx || hasX) grec[R::Z + c] = z;
-                    if (isx && hasX) grec[R::PI + w] = pin;
-                    if (b >= 0) {
-                        grec[R::LAM + b] = ll; grec[R::LAM + NB2 + b] = lu;
-                        grec[R::T + b] = tl;   grec[R::T + NB2 + b] = tu;
+                } else if (L.r - XYL < 2) {
+                    // pose components x, y: unit columns of J, no bounds
+#pragma unroll
+                    for (int e = 0; e < XY_PER; e++) {
+                        const int j = L.r - XYL + e;
+                        if (j >= 2) continue;
+                        const double v1 = hasU ? car[j] : 0.0, v2 = hasU ? car[NX + j] : 0.0, v3 = hasU ? scr[O_PV + j] : 0.0;
+                        const double H = hasU ? tb.dt * grp_ldg(tb.W + k * NY + j) : L.We[(size_t)j * L.ldWe];
+                        const double qv = rec[R::Q + NU + j], z = rec[R::Z + NU + j], dz = rec[R::DZ + NU + j];
+                        const double pin = hasX ? rec[R::PI + j] : 0.0;
+                        const double r = qv + H * z - pin + v1 + H * dz + v2;
+                        const double pin_n = hasX ? pin + a_step * r : 0.0;
+                        const double zn = z + a_step * dz;
+                        double g = qv + H * zn - pin_n + (v1 + a_step * v2);
+                        if (hasX) L.ng = fmax(L.ng, fabs(g));
+                        g += v3;
+                        grec[R::Z + NU + j] = zn;
+                        grec[R::PI + j] = pin_n;
+                        carn[j] = pin; carn[NX + j] = hasX ? r : 0.0; carn[2 * NX + j] = zn;
+                        scr[O_GX + j] = g; scr[O_DGX + j] = H + o.reg_prim;
                     }
-                    scr[O_ZB + c] = z;
-                    if (isx) { carn[w] = pi_old; carn[NX + w] = dpi_new; carn[2 * NX + w] = z; }
+                }
+                if (hasU && L.r < NX) {
+                    // dynamics residual, row r, at the new iterate (recomputed from the record: no exchange)
+                    const double rb = jrow(L.r, [&](int c) { return rec[R::Z + c] + a_step * rec[R::DZ + c]; },
+                                           [&](int j) { return rec[R::Z + NU + j] + a_step * rec[R::DZ + NU + j]; }, rec + R::E, ltk)
+                                      + rec[R::B0 + L.r] - car[2 * NX + L.r];
+                    L.nb = fmax(L.nb, fabs(rb));
+                    scr[O_RB + L.r] = rb;
+                    grec[R::RB + L.r] = rb;
                 }
             GRP_PHASE_END
             if (!hasU) {
@@ -425,61 +486,46 @@ struct Grp {
                 GRP_PHASE_BEGIN(lanes)
                     if (!L.run || L.r >= NX) continue;
                     double* scr = sm + L.slot * SLOT_D;
-                    const double pd = L.We + o.reg_prim + L.Gam[0];
+                    const double pd = scr[O_DGX + L.r];
 #pragma unroll
                     for (int i = 0; i < NX; i++) L.Pc[i] = pd * sel(i == L.r);
-                    scr[O_PV + L.r] = L.g[0];
+                    scr[O_PV + L.r] = scr[O_GX + L.r];
                 GRP_PHASE_END
                 continue;
             }
-            // ---- B2: dynamics residual (row r) and row r of P * [A B] ----------------------------
+            // ---- B4: column of M = J'PJ + D; gradient += J'P rb ------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.slot * SLOT_D;
-                const double* rec = scr + O_IN + buf * R::NREC;
+                double rbv[NX];
 #pragma unroll
-                for (int i = 0; i < 3 * NC; i++) L.Ef[i] = rec[R::E + i];
-#pragma unroll
-                for (int i = 0; i < 4 * NV; i++) L.lt[i] = grp_ldg(ltk + i);
-                if (L.r >= NX) continue;
-                const double* car = scr + O_CAR + (s & 1) * 3 * NX;
-                const double rb = jrow_dot(L.r, scr + O_ZB, scr + O_ZB + NU, rec + R::E, ltk) + rec[R::B0 + L.r] - car[2 * NX + L.r];
-                L.nb = fmax(L.nb, fabs(rb));
-                scr[O_RB + L.r] = rb;
-                rec_of(ws, L.li, k)[R::RB + L.r] = rb;
-#pragma unroll
-                for (int w = 0; w < NZ; w++)
-                    if (hasX || w >= NX) scr[O_PBA + L.r * NZ + w] = jcol_dot_r(w, L.Pc, L.Ef, L.lt);
-            GRP_PHASE_END
-            // ---- B4: column of M = J'PJ + D per component; gradient += J'(P rb + p) --------------
-            GRP_PHASE_BEGIN(lanes)
-                if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
-#pragma unroll
-                for (int t = 0; t < CW; t++) {
-                    const int w = L.r + t * G;
-                    if (w >= NZ) continue;
-                    const bool isx = w < NX;
-                    if (isx && !hasX) continue;
+                for (int i = 0; i < NX; i++) rbv[i] = scr[O_RB + i];
+                if (hasX && L.r < NX) {
                     double col[NX];
 #pragma unroll
-                    for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + w];
-                    double gg = L.g[t] + jcol_dot(w, scr + O_PV, scr + O_IN + buf * R::NREC + R::E, ltk);
+                    for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + L.r];
+                    double gg = scr[O_GX + L.r];
 #pragma unroll
-                    for (int i = 0; i < NX; i++) gg += col[i] * scr[O_RB + i];
-                    L.g[t] = gg;
-                    if (isx) {
-                        const double dg = L.H[t] + o.reg_prim + L.Gam[t];
+                    for (int i = 0; i < NX; i++) gg += col[i] * rbv[i];
+                    L.gx = gg;
+                    const double dg = scr[O_DGX + L.r];
 #pragma unroll
-                        for (int wp = 0; wp < NZ; wp++) L.Mx[wp] = jcol_dot_r(wp, col, L.Ef, L.lt) + (wp < NX ? dg * sel(wp == w) : 0.0);
-                    } else {
-                        const int a = w - NX;
+                    for (int wp = 0; wp < NZ; wp++) L.Mx[wp] = jcol_dot_r(wp, col, L.Ef, L.lt) + (wp < NX ? dg * sel(wp == L.r) : 0.0);
+                }
+                if (L.r >= ULB && L.r < ULB + ULN) {
 #pragma unroll
-                        for (int ap = 0; ap < NV; ap++) {
-                            double m = jcol_dot_r(NX + ap, col, L.Ef, L.lt);
-                            if (ap == a) m += L.H[t] + o.reg_prim + L.Gam[t];
-                            scr[O_MUU + ap * NV + a] = m;
-                        }
+                    for (int e = 0; e < NV / ULN; e++) {
+                        const int a = (L.r - ULB) * (NV / ULN) + e;
+                        double col[NX];
+#pragma unroll
+                        for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + NX + a];
+                        double gg = scr[O_GU + a];
+#pragma unroll
+                        for (int i = 0; i < NX; i++) gg += col[i] * rbv[i];
+                        const double dg = scr[O_DGU + a];
+#pragma unroll
+                        for (int ap = 0; ap < NV; ap++)
+                            scr[O_MUU + ap * NV + a] = jcol_dot_r(NX + ap, col, L.Ef, L.lt) + dg * sel(ap == a);
                         scr[O_GU + a] = gg;
                     }
                 }
@@ -544,7 +590,7 @@ struct Grp {
                     for (int a = 0; a < NV; a++) sacc -= scr[O_KB + a * NX + i] * L.Kc[a];
                     L.Pc[i] = sacc;
                 }
-                double pvn = L.g[0];
+                double pvn = L.gx;
 #pragma unroll
                 for (int a = 0; a < NV; a++) pvn -= L.Kc[a] * L.lh[a];
                 scr[O_PV + L.r] = pvn;
@@ -568,7 +614,7 @@ struct Grp {
             if (L.run) {
                 double* scr = sm + L.slot * SLOT_D;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
-                issue<KIND>(L, ws, scr, 0, 0);
+                issue<KIND>(L, rec_of(ws, L.li, 0), scr + O_IN);
             }
             grp_cp_commit();
         GRP_PHASE_END
@@ -576,39 +622,38 @@ struct Grp {
         for (int k = 0; k <= NSTAGE; k++) {
             const int buf = k & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lti + (hasU ? k : 0) * 4 * NV;
+            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
-            // ---- F1: s_a = lh_a + K_a . dx --------------------------------------------------------
+            // ---- F1: prefetch; s_a = lh_a + K_a . dx on the first NV lanes ------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.slot * SLOT_D;
-                if (k < NSTAGE) issue<KIND>(L, ws, scr, k + 1, buf ^ 1);
+                if (k < NSTAGE) issue<KIND>(L, rec_of(ws, L.li, k + 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
-                if (!hasU) continue;
+                if (!hasU || L.r >= NV) continue;
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* dx = scr + O_CAR + (k & 1) * NX;
+                const int a = L.r;
+                double s0 = rec[(DELTA ? R::LHD : R::LH) + a], s1 = 0.0;
+                if (hasX) {
 #pragma unroll
-                for (int t = 0; t < CW; t++) {
-                    const int w = L.r + t * G;
-                    if (w < NX || w >= NZ) continue;
-                    const int a = w - NX;
-                    double sacc = rec[(DELTA ? R::LHD : R::LH) + a];
-                    if (hasX) {
-#pragma unroll
-                        for (int j = 0; j < NX; j++) sacc += rec[R::KH + a * NX + j] * dx[j];
+                    for (int j = 0; j < NX; j++) {
+                        if (j & 1) s1 += rec[R::KH + a * NX + j] * dx[j];
+                        else s0 += rec[R::KH + a * NX + j] * dx[j];
                     }
-                    scr[O_GU + a] = sacc;
                 }
+                scr[O_GU + a] = s0 + s1;
             GRP_PHASE_END
-            // ---- F2: du (every lane), own step component, bound pair, next dx (row r) ----------------
+            // ---- F2: du (every lane); one constraint per lane: ratio test, mu sums; step stores;
+            //      next dx (row r) -----------------------------------------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.slot * SLOT_D;
                 const double* rec = scr + O_IN + buf * R::NREC;
                 double* grec = rec_of(ws, L.li, k);
-                const double sigmu = L.c.sigmu;
+                const double* dx = scr + O_CAR + (k & 1) * NX;
 #pragma unroll
                 for (int a = 0; a < NV; a++) L.du[a] = 0.0;
                 if (hasU) {
@@ -620,46 +665,44 @@ struct Grp {
                         L.du[a] = sacc * rec[R::LUU + a * (a + 1) / 2 + a];
                     }
                 }
+                auto du_of = [&](int c) { double v = 0.0;
 #pragma unroll
-                for (int t = 0; t < CW; t++) {
-                    const int w = L.r + t * G;
-                    if (w >= NZ) continue;
-                    const bool isx = w < NX;
-                    const int c = zc(w), b = bnd(w);
-                    double dzw = 0.0;
-                    if (isx) dzw = L.dxr;
-                    else {
-#pragma unroll
-                        for (int a = 0; a < NV; a++) dzw += L.du[a] * sel(a == w - NX);
-                    }
-                    if (!DELTA) grec[R::DZA + c] = dzw;
-                    else { dzw += rec[R::DZA + c]; grec[R::DZ + c] = dzw; }
-                    const bool act = b >= 0 && (isx ? hasX : hasU);
-                    if (act) {
-                        const double ll = rec[R::LAM + b], lu = rec[R::LAM + NB2 + b];
-                        const double tl = rec[R::T + b], tu = rec[R::T + NB2 + b];
-                        const double zb = rec[R::Z + c];
-                        const double rd_l = rec[R::DLB + b] - zb + tl, rd_u = -rec[R::DUB + b] + zb + tu;
-                        double rm_l = ll * tl - o.tau_min, rm_u = lu * tu - o.tau_min;
-                        if (DELTA) {
-                            rm_l += mcw * rec[R::MC + b] - sigmu;
-                            rm_u += mcw * rec[R::MC + NB2 + b] - sigmu;
-                        }
-                        const double dt_l = dzw - rd_l, dt_u = -dzw - rd_u;
-                        const double dl_l = -(ll * dt_l + rm_l) / tl, dl_u = -(lu * dt_u + rm_u) / tu;
-                        if (!DELTA) { grec[R::MC + b] = dt_l * dl_l; grec[R::MC + NB2 + b] = dt_u * dl_u; }
-                        if (L.alpha * dl_l > ll) L.alpha = ll / dl_l;
-                        if (L.alpha * dt_l > tl) L.alpha = tl / dt_l;
-                        if (L.alpha * dl_u > lu) L.alpha = lu / dl_u;
-                        if (L.alpha * dt_u > tu) L.alpha = tu / dt_u;
-                        L.S0 += ll * tl + lu * tu;
-                        L.S1 += ll * dt_l + tl * dl_l + lu * dt_u + tu * dl_u;
-                        L.S2 += dl_l * dt_l + dl_u * dt_u;
+                    for (int a = 0; a < NV; a++) v += L.du[a] * sel(a == c);
+                    return v; };
+                if (L.r < NCT) {
+                    const int c = L.r;
+                    const bool actc = (L.ct_u >= 0) ? hasU : hasX;
+                    if (actc) {
+                        double dzw = L.ct_x >= 0 ? dx[L.ct_x >= 0 ? L.ct_x : 0] : du_of(L.ct_u);
+                        if (DELTA) dzw += rec[R::DZA + L.ct_z];
+                        const double sg = L.ct_s;
+                        const double lam = rec[R::LAM + c], t = rec[R::T + c], zb = rec[R::Z + L.ct_z];
+                        const double rd = sg * (rec[R::DLB + c] - zb) + t;
+                        double rm = lam * t - o.tau_min;
+                        if (DELTA) rm += mcw * rec[R::MC + c] - L.c.sigmu;
+                        const double dt = sg * dzw - rd;
+                        const double dl = -(lam * dt + rm) / t;
+                        if (!DELTA) grec[R::MC + c] = dt * dl;
+                        if (L.alpha * dl > lam) L.alpha = lam / dl;
+                        if (L.alpha * dt > t) L.alpha = t / dt;
+                        L.S0 += lam * t;
+                        L.S1 += lam * dt + t * dl;
+                        L.S2 += dl * dt;
                     }
                 }
+                // step components -> DZA (predictor) / DZ (final): lane j stores state j, lane a < NV control a too
+                if (L.r < NX) {
+                    double dzw = L.dxr;
+                    if (!DELTA) grec[R::DZA + NU + L.r] = dzw;
+                    else grec[R::DZ + NU + L.r] = dzw + rec[R::DZA + NU + L.r];
+                }
+                if (L.r < NV) {
+                    double dzw = du_of(L.r);
+                    if (!DELTA) grec[R::DZA + L.r] = dzw;
+                    else grec[R::DZ + L.r] = dzw + rec[R::DZA + L.r];
+                }
                 if (hasU && L.r < NX) {
-                    const double* dx = scr + O_CAR + (k & 1) * NX;
-                    double xn = jrow_dot(L.r, L.du, dx, rec + R::E, ltk);
+                    double xn = jrow(L.r, du_of, [&](int j) { return dx[j]; }, rec + R::E, ltk);
                     if (!DELTA) xn += rec[R::RB + L.r];
                     L.dxr = xn;
                     scr[O_CAR + ((k & 1) ^ 1) * NX + L.r] = xn;
@@ -677,11 +720,10 @@ struct Grp {
     NMPC_HD static void sweep_Bd(Lane* lanes, double* sm, double* ws, const Tables& tb, double mcw)
     {
         GRP_PHASE_BEGIN(lanes)
-            L.dxr = 0.0;
             if (L.run) {
                 double* scr = sm + L.slot * SLOT_D;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
-                issue<SW_BD>(L, ws, scr, NSTAGE, 0);
+                issue<SW_BD>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
             grp_cp_commit();
         GRP_PHASE_END
@@ -689,31 +731,37 @@ struct Grp {
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lti + (hasU ? k : 0) * 4 * NV;
+            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
-            // ---- D1: q = J' dp + complementarity terms ---------------------------------------------
+            // ---- D1: q = J' dp + complementarity terms, one component per lane -----------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.slot * SLOT_D;
-                if (s < NSTAGE) issue<SW_BD>(L, ws, scr, k - 1, buf ^ 1);
+                if (s < NSTAGE) issue<SW_BD>(L, rec_of(ws, L.li, k - 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* dp = scr + O_CAR + (s & 1) * NX;
-                const double sigmu = L.c.sigmu;
-#pragma unroll
-                for (int t = 0; t < CW; t++) {
-                    const int w = L.r + t * G;
-                    if (w >= NZ) continue;
-                    const bool isx = w < NX;
-                    const int b = bnd(w);
-                    double qv = hasU ? jcol_dot(w, dp, rec + R::E, ltk) : 0.0;
-                    if (b >= 0 && (isx ? hasX : hasU)) {
-                        const double tl = rec[R::T + b], tu = rec[R::T + NB2 + b];
-                        qv += (mcw * rec[R::MC + b] - sigmu) / tl - (mcw * rec[R::MC + NB2 + b] - sigmu) / tu;
+                if (L.r < NC) {
+                    const int q = L.r;
+                    const bool isx = L.cq_x >= 0;
+                    double qv = 0.0;
+                    if (hasU) {
+                        const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
+                        qv = jt_comp(L, e0, e1, e2, grp_ldg(ltk + L.cq_k1), grp_ldg(ltk + L.cq_k2), dp);
                     }
-                    if (isx) L.g[0] = qv; else scr[O_GU + (w - NX)] = qv;
+                    if (L.cq_bl < NCT && (isx ? hasX : hasU)) {
+                        const double tl = rec[R::T + L.cq_bl], tu = rec[R::T + L.cq_bu];
+                        qv += (mcw * rec[R::MC + L.cq_bl] - L.c.sigmu) / tl - (mcw * rec[R::MC + L.cq_bu] - L.c.sigmu) / tu;
+                    }
+                    if (isx) scr[O_GX + L.cq_x] = qv; else scr[O_GU + L.cq_z] = qv;
+                } else if (L.r - XYL < 2) {
+#pragma unroll
+                    for (int e = 0; e < XY_PER; e++) {
+                        const int j = L.r - XYL + e;
+                        if (j < 2) scr[O_GX + j] = hasU ? dp[j] : 0.0;
+                    }
                 }
             GRP_PHASE_END
             // ---- D2: lh = L^-1 q_u (every lane), dp = q_x - K' lh -------------------------------------
@@ -723,7 +771,6 @@ struct Grp {
                 const double* rec = scr + O_IN + buf * R::NREC;
                 double* dpn = scr + O_CAR + ((s & 1) ^ 1) * NX;
                 if (hasU) {
-                    double* grec = rec_of(ws, L.li, k);
 #pragma unroll
                     for (int a = 0; a < NV; a++) {
                         double sacc = scr[O_GU + a];
@@ -732,16 +779,17 @@ struct Grp {
                         L.lh[a] = sacc * rec[R::LUU + a * (a + 1) / 2 + a];
                     }
                     if (L.r == WL) {
+                        double* grec = rec_of(ws, L.li, k);
 #pragma unroll
                         for (int a = 0; a < NV; a++) grec[R::LHD + a] = L.lh[a];
                     }
                     if (hasX && L.r < NX) {
-                        double sacc = L.g[0];
+                        double sacc = scr[O_GX + L.r];
 #pragma unroll
                         for (int a = 0; a < NV; a++) sacc -= rec[R::KH + a * NX + L.r] * L.lh[a];
                         dpn[L.r] = sacc;
                     }
-                } else if (L.r < NX) dpn[L.r] = L.g[0];
+                } else if (L.r < NX) dpn[L.r] = scr[O_GX + L.r];
             GRP_PHASE_END
         }
     }
@@ -767,7 +815,7 @@ struct Grp {
                     const int idx = *reinterpret_cast<const int*>(sm + L.slot * SLOT_D + O_RED);
                     if (idx < n) {
                         L.act = true; L.first = true; L.li = idx; L.c.init(true);
-                        L.We = L.r < NX ? (We_inst ? We_inst[(size_t)L.r * ldWe + i0 + idx] : grp_ldg(tb.We + L.r)) : 0.0;
+                        if (We_inst) { L.We = We_inst + i0 + idx; L.ldWe = ldWe; } else { L.We = tb.We; L.ldWe = 1; }
                     }
                 }
                 L.run = L.act;
@@ -789,7 +837,8 @@ struct Grp {
                         out.qp_status[i] = L.c.status;
                         out.qp_iter[i] = L.c.iter;
                         if (out.stats) {
-                            for (int q = 0; q < 4; q++) out.stats[(size_t)q * out.B + i] = L.c.nrm[q];
+                            out.stats[(size_t)0 * out.B + i] = L.c.nrm[0]; out.stats[(size_t)1 * out.B + i] = L.c.nrm[1];
+                            out.stats[(size_t)2 * out.B + i] = L.c.nrm[2]; out.stats[(size_t)3 * out.B + i] = L.c.nrm[3];
                             out.stats[(size_t)4 * out.B + i] = L.c.mu;
                             out.stats[(size_t)5 * out.B + i] = L.c.lin_res;
                             out.stats[(size_t)6 * out.B + i] = (double)L.c.nfb;
@@ -845,14 +894,6 @@ struct Grp {
         for (int ln = 0; ln < GRP_NL; ln++) r = r || f(lanes[ln]);
         return r;
 #endif
-    }
-
-    NMPC_HD static void init_lane(Lane& L, int lane)
-    {
-        L.r = lane % G; L.slot = lane / G; L.li = -1;
-        L.act = false; L.first = false; L.run = false;
-        L.c.init(false);
-        L.astep = 0.0; L.We = 0.0;
     }
 };
 

@@ -40,7 +40,7 @@ static int set_err(int code, const char* what, cudaError_t e = cudaSuccess)
 // kernels
 // ------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti)
+__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti, double* __restrict__ lte)
 {
     using S = Rti<M>;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +50,9 @@ __global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __r
     for (int i = 0; i < S::NU; i++) u0[i] = 0.0;
     for (int i = 0; i < S::NP; i++) pk[i] = p[k * S::NP + i];
     S::rk4_sens(x0, u0, pk, dt, xn, Ep, out);
-    for (int i = 0; i < 4 * S::NV; i++) lti[k * 4 * S::NV + i] = out[i];
+    for (int i = 0; i < 4 * S::NV; i++) { lti[k * 4 * S::NV + i] = out[i]; lte[k * (4 * S::NV + 2) + i] = out[i]; }
+    lte[k * (4 * S::NV + 2) + 4 * S::NV] = 0.0;
+    lte[k * (4 * S::NV + 2) + 4 * S::NV + 1] = 1.0;
 }
 
 constexpr int LIN_BLOCK = 128;
@@ -159,19 +161,21 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
 }
 
 // ---- group path (rti_group.cuh): per-instance contiguous records -----------------------------
-// K1+K2 into the group layout: block = LIN_BLOCK instances of one stage; the [Q, LHD) head of every
-// record is staged in shared memory and written out as contiguous 368-byte (diff) runs.
+// K1+K2 and the interior-point cold start into the group layout: block = LING_BLOCK instances of one
+// stage; the [Q, LHD) head and the [MC, NREC) tail of every record are staged in shared memory and
+// written out as contiguous runs (368 + 496 bytes for diff).
+constexpr int LING_BLOCK = 64;
 template <class M>
-__global__ void __launch_bounds__(LIN_BLOCK)
+__global__ void __launch_bounds__(LING_BLOCK)
 k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const double* __restrict__ yref, int nyref,
               const double* __restrict__ We_inst, const double* __restrict__ x, const double* __restrict__ u, int ld,
-              Tables tb, double* __restrict__ ws)
+              Tables tb, IpmOpts o, double* __restrict__ ws)
 {
     using S = Rti<M>;
     using GR = GRec<S::NV>;
-    constexpr int HEAD = GR::LHD, ROW = HEAD | 1;           // odd row stride: conflict-free column access
+    constexpr int HEAD = GR::LHD, TAIL = GR::NREC - GR::MC, ROW = (HEAD + TAIL) | 1;   // odd row stride: conflict-free
     extern __shared__ double lin_sm[];
-    const int li = blockIdx.x * LIN_BLOCK + threadIdx.x, k = blockIdx.y;
+    const int li = blockIdx.x * LING_BLOCK + threadIdx.x, k = blockIdx.y;
     if (li < nchunk) {
         const int i = i0 + li;
         double xk[S::NX], uk[S::NU], xk1[S::NX], yr[S::NY], xb[S::NX], We[S::NX];
@@ -192,14 +196,17 @@ k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const
             for (int j = 0; j < S::NX; j++) xb[j] = x0bar[(size_t)j * B + i];
         }
         double* row = lin_sm + (size_t)threadIdx.x * ROW;
-        for (int d = 0; d < HEAD; d++) row[d] = 0.0;      // stages 0 and N fill only part of the head; padding stays defined
-        S::template linearize_stage<GR, 1>(k, xk, uk, xk1, yr, nyref, xb, tb, We, row, ws + (size_t)li * GR::inst_doubles + (size_t)k * GR::NREC);
+        for (int d = 0; d < HEAD + TAIL; d++) row[d] = 0.0;     // stages 0 and N fill only part; padding stays defined
+        double* tail = row + HEAD - GR::MC;                     // record offsets >= MC land in the tail part of the row
+        S::template linearize_stage<GR, 1>(k, xk, uk, xk1, yr, nyref, xb, tb, We, row, tail);
+        S::template coldstart_stage<GR, 1>(k, o, row, tail);
     }
     __syncthreads();
-    const int nrow = min(LIN_BLOCK, nchunk - blockIdx.x * LIN_BLOCK);
-    for (int idx = threadIdx.x; idx < nrow * HEAD; idx += LIN_BLOCK) {
-        const int r = idx / HEAD, d = idx - r * HEAD;
-        ws[(size_t)(blockIdx.x * LIN_BLOCK + r) * GR::inst_doubles + (size_t)k * GR::NREC + d] = lin_sm[(size_t)r * ROW + d];
+    const int nrow = min(LING_BLOCK, nchunk - blockIdx.x * LING_BLOCK);
+    for (int idx = threadIdx.x; idx < nrow * (HEAD + TAIL); idx += LING_BLOCK) {
+        const int r = idx / (HEAD + TAIL), d = idx - r * (HEAD + TAIL);
+        const int off = d < HEAD ? d : GR::MC + (d - HEAD);
+        ws[(size_t)(blockIdx.x * LING_BLOCK + r) * GR::inst_doubles + (size_t)k * GR::NREC + off] = lin_sm[(size_t)r * ROW + d];
     }
 }
 
@@ -407,7 +414,7 @@ struct nmpc_solver {
     std::vector<double> W, We, lbx, ubx, lbu, ubu, p;
     // device
     double *d_tab = nullptr;      // W | We | lbx | ubx | lbu | ubu | p | lti
-    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, tab_doubles;
+    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_lte, tab_doubles;
     bool tab_dirty = true, p_dirty = true;
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
     double *d_ws = nullptr;                      // tile workspace for one chunk
@@ -491,6 +498,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     s->off_ubu = off; off += (size_t)n * nv;
     s->off_p = off; off += (size_t)n * m.np;
     s->off_lti = off; off += (size_t)n * 4 * nv;
+    s->off_lte = off; off += (size_t)n * (4 * nv + 2);
     s->tab_doubles = off;
     // chunking bounds the workspace: NMPC_CHUNK instances per launch group (multiple of 32)
     int chunk = 131072;
@@ -604,7 +612,7 @@ extern "C" int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o)
 template <class M>
 static int launch_lti(nmpc_solver* s, cudaStream_t st)
 {
-    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti);
+    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti, s->d_tab + s->off_lte);
     CK(cudaGetLastError());
     return 0;
 }
@@ -612,7 +620,7 @@ static int launch_lti(nmpc_solver* s, cudaStream_t st)
 static int upload_tables(nmpc_solver* s, cudaStream_t st)
 {
     if (!s->tab_dirty) return 0;
-    std::vector<double> h(s->tab_doubles - (size_t)NSTAGE * 4 * s->mi.nv);
+    std::vector<double> h(s->off_lti);
     memcpy(&h[s->off_W], s->W.data(), s->W.size() * 8);
     memcpy(&h[s->off_We], s->We.data(), s->We.size() * 8);
     memcpy(&h[s->off_lbx], s->lbx.data(), s->lbx.size() * 8);
@@ -638,7 +646,7 @@ static Tables make_tables(const nmpc_solver* s)
     tb.W = s->d_tab + s->off_W; tb.We = s->d_tab + s->off_We;
     tb.lbx = s->d_tab + s->off_lbx; tb.ubx = s->d_tab + s->off_ubx;
     tb.lbu = s->d_tab + s->off_lbu; tb.ubu = s->d_tab + s->off_ubu;
-    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti;
+    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.lte = s->d_tab + s->off_lte;
     tb.dt = 1.0 / 40.0;
     return tb;
 }
@@ -757,7 +765,7 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
     s->last_chunks = nchunks; s->last_launches = 0;
     k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
     s->last_launches++;
-    const size_t sm_lin = (size_t)LIN_BLOCK * (GR::LHD | 1) * sizeof(double);
+    const size_t sm_lin = (size_t)LING_BLOCK * ((GR::LHD + GR::NREC - GR::MC) | 1) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(k_linearize_g<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lin));
@@ -769,8 +777,8 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
         const int n = (B - i0) < s->chunk ? (B - i0) : s->chunk;
         cudaEvent_t* ev = &s->ev[(size_t)c * 4];
         CK(cudaEventRecord(ev[0], st));
-        dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
-        k_linearize_g<M><<<g1, LIN_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
+        dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1), g0((n + LING_BLOCK - 1) / LING_BLOCK, NSTAGE + 1);
+        k_linearize_g<M><<<g0, LING_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, o, s->d_ws);
         CK(cudaEventRecord(ev[1], st));
         const int G = s->grp_G;
         if constexpr (S::NV == 2) {

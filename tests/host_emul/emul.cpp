@@ -24,7 +24,7 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt};
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, nullptr};
     std::vector<double> tile(R::tile_doubles);
     for (int i = 0; i < B; i++) {
         std::fill(tile.begin(), tile.end(), 0.0);
@@ -78,7 +78,12 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt};
+    std::vector<double> lte(NSTAGE * GP::LTE);
+    for (int k = 0; k < NSTAGE; k++) {
+        for (int i = 0; i < 4 * NV; i++) lte[k * GP::LTE + i] = lti[k * 4 * NV + i];
+        lte[k * GP::LTE + 4 * NV] = 0.0; lte[k * GP::LTE + 4 * NV + 1] = 1.0;
+    }
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, lte.data()};
     std::vector<double> ws((size_t)B * GR::inst_doubles, 0.0);
     std::vector<double> WeT;                  // kernel layout of the per-instance terminal weights: [nx][B]
     if (We_inst) { WeT.resize((size_t)NX * B); for (int i = 0; i < B; i++) for (int j = 0; j < NX; j++) WeT[(size_t)j * B + i] = We_inst[(size_t)i * NX + j]; }
@@ -91,6 +96,7 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
             double* rec = GP::rec_of(ws.data(), i, k);
             S::template linearize_stage<GR, 1>(k, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU, xi + (k < NSTAGE ? k + 1 : k) * NX,
                                                yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei, rec, rec);
+            S::template coldstart_stage<GR, 1>(k, *o, rec, rec);
         }
     }
     std::vector<int> qs(B, -1), qi(B, 0);
