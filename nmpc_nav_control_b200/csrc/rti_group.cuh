@@ -117,6 +117,16 @@ NMPC_HD double grp_ldg(const double* p)
 #endif
 }
 
+// pins a lane-constant integer in a register: without it ptxas rematerialises role indices from
+// threadIdx (S2R + shifts + masks) at every use, ~20% of all issued instructions
+NMPC_HD int grp_pin(int v)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(v));
+#endif
+    return v;
+}
+
 struct GrpOut {            // per-instance results of K3 (global, indexed by instance of the batch)
     int* qp_status;
     int* qp_iter;
@@ -193,7 +203,7 @@ struct Grp {
 
     // ---- state of one lane (registers on the device) ----------------------------------------
     struct Lane {
-        int r, slot;              // role index in the group, slot of the warp
+        int r, so;                // role index in the group; offset (doubles) of the slot's scratch in the shared array
         int li;                   // instance (index into the chunk) of the slot, -1 = none
         bool act, first, run;     // slot has an instance / its next B sweep is the first / takes part in the current sweep
         LaneCtl c;                // replicated over the lanes of the slot
@@ -222,10 +232,11 @@ struct Grp {
         double alpha, S0, S1, S2;
     };
 
-    NMPC_HD static void init_lane(Lane& L, int lane)
+    // lane: lane of the warp; warp: index of the warp's scratch in the shared array
+    NMPC_HD static void init_lane(Lane& L, int lane, int warp)
     {
-        const int r = lane % G;
-        L.r = r; L.slot = lane / G; L.li = -1;
+        const int r = grp_pin(lane % G);
+        L.r = r; L.so = grp_pin(warp * WARP_D + (lane / G) * SLOT_D); L.li = -1;
         L.act = false; L.first = false; L.run = false;
         L.c.init(false);
         L.astep = 0.0; L.We = nullptr; L.ldWe = 0;
@@ -251,6 +262,9 @@ struct Grp {
         L.ct_u = b < NV ? b : -1;
         L.ct_x = b < NV ? -1 : 3 + b;
         L.ct_z = b < NV ? b : NU + 3 + b;
+        L.cq_z = grp_pin(L.cq_z); L.cq_x = grp_pin(L.cq_x); L.cq_y = grp_pin(L.cq_y); L.cq_bl = grp_pin(L.cq_bl); L.cq_bu = grp_pin(L.cq_bu);
+        L.cq_i1 = grp_pin(L.cq_i1); L.cq_i2 = grp_pin(L.cq_i2); L.cq_k1 = grp_pin(L.cq_k1); L.cq_k2 = grp_pin(L.cq_k2);
+        L.ct_z = grp_pin(L.ct_z); L.ct_x = grp_pin(L.ct_x); L.ct_u = grp_pin(L.ct_u);
     }
 
     NMPC_HD static double* rec_of(double* ws, int li, int k) { return ws + (size_t)li * R::inst_doubles + (size_t)k * R::NREC; }
@@ -289,11 +303,11 @@ struct Grp {
     NMPC_HD static void reduce(Lane* lanes, double* sm, int n, int nmax, GF get, PF put)
     {
         GRP_PHASE_BEGIN(lanes)
-            double* scr = sm + L.slot * SLOT_D;
+            double* scr = sm + L.so;
             for (int q = 0; q < n; q++) scr[O_RED + L.r * 8 + q] = get(L, q);
         GRP_PHASE_END
         GRP_PHASE_BEGIN(lanes)
-            const double* scr = sm + L.slot * SLOT_D;
+            const double* scr = sm + L.so;
             for (int q = 0; q < n; q++) {
                 double v = scr[O_RED + q];
                 for (int rr = 1; rr < G; rr++) {
@@ -338,7 +352,7 @@ struct Grp {
         GRP_PHASE_BEGIN(lanes)
             L.ng = L.nb = L.nd = L.nm = L.musum = L.lru = 0.0;
             if (L.run) {
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 if (L.r < NX) { scr[O_CAR + L.r] = 0.0; scr[O_CAR + NX + L.r] = 0.0; scr[O_CAR + 2 * NX + L.r] = 0.0; scr[O_PV + L.r] = 0.0; }
                 if (L.r < 4) scr[O_CB + 4 * NCT + L.r] = 0.0;
                 issue<SW_B>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
@@ -356,7 +370,7 @@ struct Grp {
             // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 double* grec = rec_of(ws, L.li, k);
                 if (s < NSTAGE) issue<SW_B>(L, grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
@@ -407,7 +421,7 @@ struct Grp {
             //      the dynamics residual --------------------------------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 double* grec = rec_of(ws, L.li, k);
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
@@ -485,7 +499,7 @@ struct Grp {
                 // terminal stage: P = diag(We + reg + Gamma), p = g
                 GRP_PHASE_BEGIN(lanes)
                     if (!L.run || L.r >= NX) continue;
-                    double* scr = sm + L.slot * SLOT_D;
+                    double* scr = sm + L.so;
                     const double pd = scr[O_DGX + L.r];
 #pragma unroll
                     for (int i = 0; i < NX; i++) L.Pc[i] = pd * sel(i == L.r);
@@ -496,7 +510,7 @@ struct Grp {
             // ---- B4: column of M = J'PJ + D; gradient += J'P rb ------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 double rbv[NX];
 #pragma unroll
                 for (int i = 0; i < NX; i++) rbv[i] = scr[O_RB + i];
@@ -533,7 +547,7 @@ struct Grp {
             // ---- B5: Cholesky of the control block (every lane), lh, column r of K ----------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 double* grec = rec_of(ws, L.li, k);
                 double Luu[NLU];
 #pragma unroll
@@ -582,7 +596,7 @@ struct Grp {
             // ---- B6: Schur complement -> column r of this stage's cost-to-go, and its gradient -----
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run || L.r >= NX) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
 #pragma unroll
                 for (int i = 0; i < NX; i++) {
                     double sacc = L.Mx[i];
@@ -612,7 +626,7 @@ struct Grp {
         GRP_PHASE_BEGIN(lanes)
             L.alpha = -1.0; L.S0 = L.S1 = L.S2 = 0.0; L.dxr = 0.0;
             if (L.run) {
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
                 issue<KIND>(L, rec_of(ws, L.li, 0), scr + O_IN);
             }
@@ -629,7 +643,7 @@ struct Grp {
             // ---- F1: prefetch; s_a = lh_a + K_a . dx on the first NV lanes ------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 if (k < NSTAGE) issue<KIND>(L, rec_of(ws, L.li, k + 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 if (!hasU || L.r >= NV) continue;
@@ -650,7 +664,7 @@ struct Grp {
             //      next dx (row r) -----------------------------------------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 const double* rec = scr + O_IN + buf * R::NREC;
                 double* grec = rec_of(ws, L.li, k);
                 const double* dx = scr + O_CAR + (k & 1) * NX;
@@ -721,7 +735,7 @@ struct Grp {
     {
         GRP_PHASE_BEGIN(lanes)
             if (L.run) {
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
                 issue<SW_BD>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
@@ -738,7 +752,7 @@ struct Grp {
             // ---- D1: q = J' dp + complementarity terms, one component per lane -----------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 if (s < NSTAGE) issue<SW_BD>(L, rec_of(ws, L.li, k - 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 const double* rec = scr + O_IN + buf * R::NREC;
@@ -767,7 +781,7 @@ struct Grp {
             // ---- D2: lh = L^-1 q_u (every lane), dp = q_x - K' lh -------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
-                double* scr = sm + L.slot * SLOT_D;
+                double* scr = sm + L.so;
                 const double* rec = scr + O_IN + buf * R::NREC;
                 double* dpn = scr + O_CAR + ((s & 1) ^ 1) * NX;
                 if (hasU) {
@@ -806,13 +820,13 @@ struct Grp {
             // ---- refill free slots --------------------------------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.act && L.r == 0) {
-                    int* q = reinterpret_cast<int*>(sm + L.slot * SLOT_D + O_RED);
+                    int* q = reinterpret_cast<int*>(sm + L.so + O_RED);
                     *q = grp_fetch_add(next);
                 }
             GRP_PHASE_END
             GRP_PHASE_BEGIN(lanes)
                 if (!L.act) {
-                    const int idx = *reinterpret_cast<const int*>(sm + L.slot * SLOT_D + O_RED);
+                    const int idx = *reinterpret_cast<const int*>(sm + L.so + O_RED);
                     if (idx < n) {
                         L.act = true; L.first = true; L.li = idx; L.c.init(true);
                         if (We_inst) { L.We = We_inst + i0 + idx; L.ldWe = ldWe; } else { L.We = tb.We; L.ldWe = 1; }

@@ -221,10 +221,9 @@ k_ipm_group(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ld
 {
     using GP = Grp<M, G>;
     extern __shared__ __align__(16) double grp_sm[];
-    double* sm = grp_sm + (size_t)(threadIdx.x >> 5) * GP::WARP_D;
     typename GP::Lane L;
-    GP::init_lane(L, threadIdx.x & 31);
-    GP::run_warp(&L, sm, ws, i0, n, next, tb, We_inst, ldWe, o, out);
+    GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
+    GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out);
 }
 
 // K4 from the group layout

@@ -107,7 +107,7 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
     for (int wp = 0; wp < nwarps; wp++) {
         std::vector<typename GP::Lane> lanes(32);
         std::vector<double> sm(GP::WARP_D, 0.0);
-        for (int l = 0; l < 32; l++) GP::init_lane(lanes[l], l);
+        for (int l = 0; l < 32; l++) GP::init_lane(lanes[l], l, 0);
         GP::run_warp(lanes.data(), sm.data(), ws.data(), 0, B, &next, tb, We_inst ? WeT.data() : nullptr, B, *o, out);
     }
     for (int i = 0; i < B; i++) {
