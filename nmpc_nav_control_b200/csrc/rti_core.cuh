@@ -119,7 +119,7 @@ struct Tables {
     const double* p;      // [N][NP]
     const double* lti;    // [N][4*NV] av, ar, au, ru per channel (written by the LTI set-up kernel)
     double dt;
-    const double* lte;    // [N][4*NV+2] the same followed by the constants 0 and 1 (group path: table-driven lane roles)
+    const double* stg;    // [N+1][TROW] group path: per stage av|ar|au|ru, the constants 0 and 1, then the diagonal of W; rows padded to even (Grp::TROW)
 };
 
 template <int NV>

@@ -127,6 +127,16 @@ NMPC_HD int grp_pin(int v)
     return v;
 }
 
+// 1/sqrt(d): the device intrinsic (MUFU.RSQ64H + Newton steps, <= 1 ulp) instead of sqrt + divide
+NMPC_HD double grp_rsqrt(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(d);
+#else
+    return 1.0 / sqrt(d);
+#endif
+}
+
 struct GrpOut {            // per-instance results of K3 (global, indexed by instance of the batch)
     int* qp_status;
     int* qp_iter;
@@ -172,13 +182,21 @@ struct Grp {
     static constexpr int O_MUU = O_PBA + NX * NZ;         // [NV][NV]
     static constexpr int O_KB = O_MUU + NV * NV;          // [NV][NX]
     static constexpr int O_DUMP = O_KB + NV * NX;         // 4    target of role-masked stores
+    static constexpr int O_AST = O_DUMP + 2;              //      damped step handed from lane 0 to the slot
+    static constexpr int O_CTL = O_DUMP + 4;              // the slot's LaneCtl (owned by lane 0 between the sweeps)
+    static constexpr int CTL_D = (int)((sizeof(LaneCtl) + 7) / 8);
     static constexpr int O_RED = O_IN;                    // [G][8] reductions at the end of a sweep / queue hand-out (the record image is dead there)
-    static constexpr int O_END = O_DUMP + 4;
+    static constexpr int O_END = O_CTL + CTL_D;
     static_assert(G * 8 <= 2 * R::NREC, "reduction buffer must fit into the record image");
     // slot stride: even (16-byte copies) and = 8 mod 16 so that equal offsets of neighbouring slots
     // fall into different bank groups
     static constexpr int SLOT_D = ((O_END + 15) / 16) * 16 + 8;
-    static constexpr int WARP_D = SLOT_D * NSLOT;         // doubles of shared memory per warp
+    // per-warp image of the stage table row (double buffered like the records): [lte (4NV+2) | W (NY)], rows padded
+    static constexpr int T_W = (LTE + 1) & ~1;            // offset of the weights in a row
+    static constexpr int TROW = T_W + ((NY + 1) & ~1);
+    static constexpr int O_TAB = SLOT_D * NSLOT;
+    static constexpr int WARP_D = SLOT_D * NSLOT + 2 * TROW;   // doubles of shared memory per warp
+    static_assert(TROW / 2 <= 32, "one 16-byte chunk of the stage table per lane");
 
     // static-index products with J = [A B] (registers only): (column w of J) . v, w in [x; u] order
     NMPC_HD static double jcol_dot_r(int w, const double* v, const double* E, const double* lt)
@@ -206,8 +224,9 @@ struct Grp {
         int r, so;                // role index in the group; offset (doubles) of the slot's scratch in the shared array
         int li;                   // instance (index into the chunk) of the slot, -1 = none
         bool act, first, run;     // slot has an instance / its next B sweep is the first / takes part in the current sweep
-        LaneCtl c;                // replicated over the lanes of the slot
+        double sigmu, mcw;        // copies of the slot's LaneCtl fields the sweeps use (LaneCtl itself lives in the scratch)
         double astep;             // damped step applied by the running B sweep
+        int to, wl;               // offset of the warp's stage-table image; lane of the warp
         const double* We;         // terminal weights of the instance: We[j * ldWe]
         int ldWe;
         // component role (generic components q = r < NC)
@@ -237,8 +256,9 @@ struct Grp {
     {
         const int r = grp_pin(lane % G);
         L.r = r; L.so = grp_pin(warp * WARP_D + (lane / G) * SLOT_D); L.li = -1;
+        L.to = grp_pin(warp * WARP_D + O_TAB); L.wl = grp_pin(lane);
         L.act = false; L.first = false; L.run = false;
-        L.c.init(false);
+        L.sigmu = 0.0; L.mcw = 1.0;
         L.astep = 0.0; L.We = nullptr; L.ldWe = 0;
         // component role: E column q = r -> theta | actual c | ref c | u a
         L.cq_z = 0; L.cq_x = -1; L.cq_y = 0; L.cq_bl = NCT; L.cq_bu = NCT;
@@ -278,6 +298,12 @@ struct Grp {
     }
 
     enum { SW_B = 0, SW_F = 1, SW_BD = 2, SW_FD = 3 };
+
+    // the stage-table row of stage k into image `buf` of the warp (every lane of the warp, running slot or not)
+    NMPC_HD static void issue_tab(const Lane& L, double* sm, const Tables& tb, int k, int buf)
+    {
+        if (2 * L.wl < TROW) grp_cp16(sm + L.to + buf * TROW + 2 * L.wl, tb.stg + (size_t)k * TROW + 2 * L.wl);
+    }
 
     template <int KIND>
     NMPC_HD static void issue(const Lane& L, const double* src, double* dst)
@@ -338,8 +364,8 @@ struct Grp {
             return s0 + s1;
         }
         const int c = i < 3 + NV ? i - 3 : i - 3 - NV;
-        if (i < 3 + NV) return grp_ldg(lt + c) * zx(3 + c) + grp_ldg(lt + NV + c) * zx(3 + NV + c) + grp_ldg(lt + 2 * NV + c) * zu(c);
-        return zx(3 + NV + c) + grp_ldg(lt + 3 * NV + c) * zu(c);
+        if (i < 3 + NV) return lt[c] * zx(3 + c) + lt[NV + c] * zx(3 + NV + c) + lt[2 * NV + c] * zu(c);
+        return zx(3 + NV + c) + lt[3 * NV + c] * zu(c);
     }
 
     // =========================================================================================
@@ -357,19 +383,21 @@ struct Grp {
                 if (L.r < 4) scr[O_CB + 4 * NCT + L.r] = 0.0;
                 issue<SW_B>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
+            issue_tab(L, sm, tb, NSTAGE, 0);
             grp_cp_commit();
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
             // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
             GRP_PHASE_BEGIN(lanes)
-                if (!L.run) continue;
+                if (s < NSTAGE) issue_tab(L, sm, tb, k - 1, buf ^ 1);
+                if (!L.run) { grp_cp_commit(); continue; }
+                const double* ltk = sm + L.to + buf * TROW;
                 double* scr = sm + L.so;
                 double* grec = rec_of(ws, L.li, k);
                 if (s < NSTAGE) issue<SW_B>(L, grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
@@ -385,7 +413,7 @@ struct Grp {
                         const double dbd = rec[R::DLB + c], z = rec[R::Z + L.ct_z], dz = rec[R::DZ + L.ct_z];
                         const double lam = rec[R::LAM + c], t = rec[R::T + c], mc = rec[R::MC + c];
                         const double rd = sg * (dbd - z) + t;
-                        const double rm = lam * t - o.tau_min + L.c.mcw * mc - L.c.sigmu;
+                        const double rm = lam * t - o.tau_min + L.mcw * mc - L.sigmu;
                         const double dt = sg * dz - rd;
                         const double dlam = -(lam * dt + rm) / t;
                         const double lam_n = lam + a_step * dlam, t_n = t + a_step * dt, zn = z + a_step * dz;
@@ -409,7 +437,7 @@ struct Grp {
 #pragma unroll
                     for (int i = 0; i < 3 * NC; i++) L.Ef[i] = rec[R::E + i];
 #pragma unroll
-                    for (int i = 0; i < 4 * NV; i++) L.lt[i] = grp_ldg(ltk + i);
+                    for (int i = 0; i < 4 * NV; i++) L.lt[i] = ltk[i];
                     if (L.r < NX) {
 #pragma unroll
                         for (int w = 0; w < NZ; w++)
@@ -426,6 +454,7 @@ struct Grp {
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
                 double* carn = scr + O_CAR + ((s & 1) ^ 1) * 3 * NX;
+                const double* ltk = sm + L.to + buf * TROW;
                 const double a_step = L.astep;
                 if (L.r < NC) {
                     // generic component: column q = r of the pose rows E
@@ -433,11 +462,11 @@ struct Grp {
                     const bool isx = L.cq_x >= 0;
                     const bool has = isx ? hasX : hasU;
                     const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
-                    const double k1 = grp_ldg(ltk + L.cq_k1), k2 = grp_ldg(ltk + L.cq_k2);
+                    const double k1 = ltk[L.cq_k1], k2 = ltk[L.cq_k2];
                     const double v1 = jt_comp(L, e0, e1, e2, k1, k2, car);
                     const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
                     const double v3 = jt_comp(L, e0, e1, e2, k1, k2, scr + O_PV);
-                    const double H = hasU ? tb.dt * grp_ldg(tb.W + k * NY + L.cq_y) : (isx ? L.We[(size_t)L.cq_x * L.ldWe] : 0.0);
+                    const double H = hasU ? tb.dt * ltk[T_W + L.cq_y] : (isx ? L.We[(size_t)L.cq_x * L.ldWe] : 0.0);
                     const double qv = rec[R::Q + L.cq_z], z = rec[R::Z + L.cq_z], dz = rec[R::DZ + L.cq_z];
                     const bool haspi = isx && hasX;
                     const double pin = haspi ? rec[R::PI + (isx ? L.cq_x : 0)] : 0.0;
@@ -470,7 +499,7 @@ struct Grp {
                         const int j = L.r - XYL + e;
                         if (j >= 2) continue;
                         const double v1 = hasU ? car[j] : 0.0, v2 = hasU ? car[NX + j] : 0.0, v3 = hasU ? scr[O_PV + j] : 0.0;
-                        const double H = hasU ? tb.dt * grp_ldg(tb.W + k * NY + j) : L.We[(size_t)j * L.ldWe];
+                        const double H = hasU ? tb.dt * ltk[T_W + j] : L.We[(size_t)j * L.ldWe];
                         const double qv = rec[R::Q + NU + j], z = rec[R::Z + NU + j], dz = rec[R::DZ + NU + j];
                         const double pin = hasX ? rec[R::PI + j] : 0.0;
                         const double r = qv + H * z - pin + v1 + H * dz + v2;
@@ -555,7 +584,7 @@ struct Grp {
                     double d = scr[O_MUU + a * NV + a];
 #pragma unroll
                     for (int c = 0; c < a; c++) d -= Luu[a * (a + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
-                    const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                    const double inv = d > 0.0 ? grp_rsqrt(d) : 0.0;
                     Luu[a * (a + 1) / 2 + a] = inv;
 #pragma unroll
                     for (int b = a + 1; b < NV; b++) {
@@ -630,19 +659,20 @@ struct Grp {
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
                 issue<KIND>(L, rec_of(ws, L.li, 0), scr + O_IN);
             }
+            issue_tab(L, sm, tb, 0, 0);
             grp_cp_commit();
         GRP_PHASE_END
 #pragma unroll 1
         for (int k = 0; k <= NSTAGE; k++) {
             const int buf = k & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
             // ---- F1: prefetch; s_a = lh_a + K_a . dx on the first NV lanes ------------------------------
             GRP_PHASE_BEGIN(lanes)
-                if (!L.run) continue;
+                if (k < NSTAGE) issue_tab(L, sm, tb, k + 1, buf ^ 1);
+                if (!L.run) { grp_cp_commit(); continue; }
                 double* scr = sm + L.so;
                 if (k < NSTAGE) issue<KIND>(L, rec_of(ws, L.li, k + 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
@@ -668,6 +698,7 @@ struct Grp {
                 const double* rec = scr + O_IN + buf * R::NREC;
                 double* grec = rec_of(ws, L.li, k);
                 const double* dx = scr + O_CAR + (k & 1) * NX;
+                const double* ltk = sm + L.to + buf * TROW;
 #pragma unroll
                 for (int a = 0; a < NV; a++) L.du[a] = 0.0;
                 if (hasU) {
@@ -693,7 +724,7 @@ struct Grp {
                         const double lam = rec[R::LAM + c], t = rec[R::T + c], zb = rec[R::Z + L.ct_z];
                         const double rd = sg * (rec[R::DLB + c] - zb) + t;
                         double rm = lam * t - o.tau_min;
-                        if (DELTA) rm += mcw * rec[R::MC + c] - L.c.sigmu;
+                        if (DELTA) rm += mcw * rec[R::MC + c] - L.sigmu;
                         const double dt = sg * dzw - rd;
                         const double dl = -(lam * dt + rm) / t;
                         if (!DELTA) grec[R::MC + c] = dt * dl;
@@ -739,19 +770,21 @@ struct Grp {
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
                 issue<SW_BD>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
+            issue_tab(L, sm, tb, NSTAGE, 0);
             grp_cp_commit();
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
-            const double* ltk = tb.lte + (hasU ? k : 0) * LTE;
             GRP_PHASE_BEGIN(lanes)
                 grp_cp_wait_all();
             GRP_PHASE_END
             // ---- D1: q = J' dp + complementarity terms, one component per lane -----------------------
             GRP_PHASE_BEGIN(lanes)
-                if (!L.run) continue;
+                if (s < NSTAGE) issue_tab(L, sm, tb, k - 1, buf ^ 1);
+                if (!L.run) { grp_cp_commit(); continue; }
+                const double* ltk = sm + L.to + buf * TROW;
                 double* scr = sm + L.so;
                 if (s < NSTAGE) issue<SW_BD>(L, rec_of(ws, L.li, k - 1), scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
@@ -763,11 +796,11 @@ struct Grp {
                     double qv = 0.0;
                     if (hasU) {
                         const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
-                        qv = jt_comp(L, e0, e1, e2, grp_ldg(ltk + L.cq_k1), grp_ldg(ltk + L.cq_k2), dp);
+                        qv = jt_comp(L, e0, e1, e2, ltk[L.cq_k1], ltk[L.cq_k2], dp);
                     }
                     if (L.cq_bl < NCT && (isx ? hasX : hasU)) {
                         const double tl = rec[R::T + L.cq_bl], tu = rec[R::T + L.cq_bu];
-                        qv += (mcw * rec[R::MC + L.cq_bl] - L.c.sigmu) / tl - (mcw * rec[R::MC + L.cq_bu] - L.c.sigmu) / tu;
+                        qv += (mcw * rec[R::MC + L.cq_bl] - L.sigmu) / tl - (mcw * rec[R::MC + L.cq_bu] - L.sigmu) / tu;
                     }
                     if (isx) scr[O_GX + L.cq_x] = qv; else scr[O_GU + L.cq_z] = qv;
                 } else if (L.r - XYL < 2) {
@@ -815,9 +848,10 @@ struct Grp {
     NMPC_HD static void run_warp(Lane* lanes, double* sm, double* ws, int i0, int n, int* next, const Tables& tb,
                                  const double* We_inst, int ldWe, const IpmOpts& o, const GrpOut& out)
     {
+#define CTL(L) (*reinterpret_cast<LaneCtl*>(sm + (L).so + O_CTL))
 #pragma unroll 1
         for (;;) {
-            // ---- refill free slots --------------------------------------------------------------
+            // ---- refill free slots; lane 0 of a slot owns its LaneCtl between the sweeps --------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.act && L.r == 0) {
                     int* q = reinterpret_cast<int*>(sm + L.so + O_RED);
@@ -828,74 +862,83 @@ struct Grp {
                 if (!L.act) {
                     const int idx = *reinterpret_cast<const int*>(sm + L.so + O_RED);
                     if (idx < n) {
-                        L.act = true; L.first = true; L.li = idx; L.c.init(true);
+                        L.act = true; L.first = true; L.li = idx;
                         if (We_inst) { L.We = We_inst + i0 + idx; L.ldWe = ldWe; } else { L.We = tb.We; L.ldWe = 1; }
+                        if (L.r == 0) CTL(L).init(true);
                     }
-                }
+                } else if (L.r == 0) sm[L.so + O_AST] = S::before_B(CTL(L));
+            GRP_PHASE_END
+            GRP_PHASE_BEGIN(lanes)
                 L.run = L.act;
                 L.astep = 0.0;
-                if (L.act && !L.first) L.astep = S::before_B(L.c);
+                if (L.act) {
+                    if (!L.first) L.astep = sm[L.so + O_AST];
+                    L.sigmu = CTL(L).sigmu; L.mcw = CTL(L).mcw;
+                }
             GRP_PHASE_END
             if (!warp_any(lanes, [](const Lane& L) { return L.act; })) break;
 
             sweep_B(lanes, sm, ws, tb, o);
             GRP_PHASE_BEGIN(lanes)
-                if (!L.act) continue;
+                if (!L.act || L.r != 0) continue;
+                LaneCtl& c = CTL(L);
                 typename S::CarryB cy;
                 cy.ng = L.ng; cy.nb = L.nb; cy.nd = L.nd; cy.nm = L.nm; cy.musum = L.musum; cy.lru = L.lru;
-                S::after_B(L.c, cy, o, L.first);
-                L.first = false;
-                if (L.c.done) {
-                    if (L.r == 0) {
-                        const int i = i0 + L.li;
-                        out.qp_status[i] = L.c.status;
-                        out.qp_iter[i] = L.c.iter;
-                        if (out.stats) {
-                            out.stats[(size_t)0 * out.B + i] = L.c.nrm[0]; out.stats[(size_t)1 * out.B + i] = L.c.nrm[1];
-                            out.stats[(size_t)2 * out.B + i] = L.c.nrm[2]; out.stats[(size_t)3 * out.B + i] = L.c.nrm[3];
-                            out.stats[(size_t)4 * out.B + i] = L.c.mu;
-                            out.stats[(size_t)5 * out.B + i] = L.c.lin_res;
-                            out.stats[(size_t)6 * out.B + i] = (double)L.c.nfb;
-                            out.stats[(size_t)7 * out.B + i] = (double)L.c.status;
-                        }
+                S::after_B(c, cy, o, L.first);
+                if (c.done) {
+                    const int i = i0 + L.li;
+                    out.qp_status[i] = c.status;
+                    out.qp_iter[i] = c.iter;
+                    if (out.stats) {
+                        out.stats[(size_t)0 * out.B + i] = c.nrm[0]; out.stats[(size_t)1 * out.B + i] = c.nrm[1];
+                        out.stats[(size_t)2 * out.B + i] = c.nrm[2]; out.stats[(size_t)3 * out.B + i] = c.nrm[3];
+                        out.stats[(size_t)4 * out.B + i] = c.mu;
+                        out.stats[(size_t)5 * out.B + i] = c.lin_res;
+                        out.stats[(size_t)6 * out.B + i] = (double)c.nfb;
+                        out.stats[(size_t)7 * out.B + i] = (double)c.status;
                     }
-                    L.act = false;
                 }
+            GRP_PHASE_END
+            GRP_PHASE_BEGIN(lanes)
+                if (L.act) { L.first = false; if (CTL(L).done) L.act = false; }
                 L.run = L.act;
             GRP_PHASE_END
             if (!warp_any(lanes, [](const Lane& L) { return L.act; })) continue;
 
             sweep_F<false>(lanes, sm, ws, tb, o, 1.0);
             GRP_PHASE_BEGIN(lanes)
-                if (!L.act) continue;
+                if (!L.act || L.r != 0) continue;
                 typename S::CarryF cy;
                 cy.alpha = L.alpha; cy.S0 = L.S0; cy.S1 = L.S1; cy.S2 = L.S2;
-                S::after_F(L.c, cy, o);
+                S::after_F(CTL(L), cy, o);
+            GRP_PHASE_END
+            GRP_PHASE_BEGIN(lanes)
+                if (L.act) L.sigmu = CTL(L).sigmu;
             GRP_PHASE_END
             sweep_Bd(lanes, sm, ws, tb, 1.0);
             sweep_F<true>(lanes, sm, ws, tb, o, 1.0);
             GRP_PHASE_BEGIN(lanes)
-                if (!L.act) continue;
+                if (!L.act || L.r != 0) continue;
                 typename S::CarryF cy;
                 cy.alpha = L.alpha; cy.S0 = L.S0; cy.S1 = L.S1; cy.S2 = L.S2;
-                S::after_Fd(L.c, cy, o);
-                L.run = L.c.fb != 0;
+                S::after_Fd(CTL(L), cy, o);
             GRP_PHASE_END
-            if (warp_any(lanes, [](const Lane& L) { return L.act && L.run; })) {
+            GRP_PHASE_BEGIN(lanes)
+                L.run = L.act && CTL(L).fb != 0;
+            GRP_PHASE_END
+            if (warp_any(lanes, [](const Lane& L) { return L.run; })) {
                 // conditional centering (rare): repeat the delta solve without the second-order term
-                GRP_PHASE_BEGIN(lanes)
-                    L.run = L.act && L.c.fb != 0;
-                GRP_PHASE_END
                 sweep_Bd(lanes, sm, ws, tb, 0.0);
                 sweep_F<true>(lanes, sm, ws, tb, o, 0.0);
                 GRP_PHASE_BEGIN(lanes)
-                    if (!L.run) continue;
+                    if (!L.run || L.r != 0) continue;
                     typename S::CarryF cy;
                     cy.alpha = L.alpha; cy.S0 = L.S0; cy.S1 = L.S1; cy.S2 = L.S2;
-                    S::after_Fd_fallback(L.c, cy);
+                    S::after_Fd_fallback(CTL(L), cy);
                 GRP_PHASE_END
             }
         }
+#undef CTL
     }
 
     template <class F>

@@ -40,7 +40,7 @@ static int set_err(int code, const char* what, cudaError_t e = cudaSuccess)
 // kernels
 // ------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti, double* __restrict__ lte)
+__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti)
 {
     using S = Rti<M>;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,9 +50,22 @@ __global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __r
     for (int i = 0; i < S::NU; i++) u0[i] = 0.0;
     for (int i = 0; i < S::NP; i++) pk[i] = p[k * S::NP + i];
     S::rk4_sens(x0, u0, pk, dt, xn, Ep, out);
-    for (int i = 0; i < 4 * S::NV; i++) { lti[k * 4 * S::NV + i] = out[i]; lte[k * (4 * S::NV + 2) + i] = out[i]; }
-    lte[k * (4 * S::NV + 2) + 4 * S::NV] = 0.0;
-    lte[k * (4 * S::NV + 2) + 4 * S::NV + 1] = 1.0;
+    for (int i = 0; i < 4 * S::NV; i++) lti[k * 4 * S::NV + i] = out[i];
+}
+
+// stage table of the group path: row k = [av|ar|au|ru (4 NV), 0, 1, pad | diagonal of W (NY), pad]; row N is zero
+__global__ void k_stage_table(int nv, int ny, int t_w, int trow, const double* __restrict__ lti, const double* __restrict__ W,
+                              double* __restrict__ stg)
+{
+    const int k = blockIdx.x, i = threadIdx.x;
+    if (i >= trow) return;
+    double v = 0.0;
+    if (k < NSTAGE) {
+        if (i < 4 * nv) v = lti[k * 4 * nv + i];
+        else if (i == 4 * nv + 1) v = 1.0;
+        else if (i >= t_w && i < t_w + ny) v = W[k * ny + (i - t_w)];
+    }
+    stg[(size_t)k * trow + i] = v;
 }
 
 constexpr int LIN_BLOCK = 128;
@@ -413,7 +426,8 @@ struct nmpc_solver {
     std::vector<double> W, We, lbx, ubx, lbu, ubu, p;
     // device
     double *d_tab = nullptr;      // W | We | lbx | ubx | lbu | ubu | p | lti
-    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_lte, tab_doubles;
+    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_stg, tab_doubles;
+    int t_w = 0, trow = 0;
     bool tab_dirty = true, p_dirty = true;
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
     double *d_ws = nullptr;                      // tile workspace for one chunk
@@ -497,7 +511,9 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     s->off_ubu = off; off += (size_t)n * nv;
     s->off_p = off; off += (size_t)n * m.np;
     s->off_lti = off; off += (size_t)n * 4 * nv;
-    s->off_lte = off; off += (size_t)n * (4 * nv + 2);
+    s->t_w = (4 * nv + 2 + 1) & ~1; s->trow = s->t_w + ((ny + 1) & ~1);
+    off = (off + 1) & ~(size_t)1;      // 16-byte aligned rows (cp.async)
+    s->off_stg = off; off += (size_t)(n + 1) * s->trow;
     s->tab_doubles = off;
     // chunking bounds the workspace: NMPC_CHUNK instances per launch group (multiple of 32)
     int chunk = 131072;
@@ -611,7 +627,7 @@ extern "C" int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o)
 template <class M>
 static int launch_lti(nmpc_solver* s, cudaStream_t st)
 {
-    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti, s->d_tab + s->off_lte);
+    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti);
     CK(cudaGetLastError());
     return 0;
 }
@@ -635,6 +651,9 @@ static int upload_tables(nmpc_solver* s, cudaStream_t st)
         if (rc) return rc;
         s->p_dirty = false;
     }
+    k_stage_table<<<NSTAGE + 1, 64, 0, st>>>(s->mi.nv, s->mi.nx + s->mi.nu, s->t_w, s->trow, s->d_tab + s->off_lti, s->d_tab + s->off_W,
+                                             s->d_tab + s->off_stg);
+    CK(cudaGetLastError());
     s->tab_dirty = false;
     return 0;
 }
@@ -645,7 +664,7 @@ static Tables make_tables(const nmpc_solver* s)
     tb.W = s->d_tab + s->off_W; tb.We = s->d_tab + s->off_We;
     tb.lbx = s->d_tab + s->off_lbx; tb.ubx = s->d_tab + s->off_ubx;
     tb.lbu = s->d_tab + s->off_lbu; tb.ubu = s->d_tab + s->off_ubu;
-    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.lte = s->d_tab + s->off_lte;
+    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.stg = s->d_tab + s->off_stg;
     tb.dt = 1.0 / 40.0;
     return tb;
 }

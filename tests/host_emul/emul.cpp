@@ -78,12 +78,13 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
     }
-    std::vector<double> lte(NSTAGE * GP::LTE);
+    std::vector<double> stg((NSTAGE + 1) * GP::TROW, 0.0);
     for (int k = 0; k < NSTAGE; k++) {
-        for (int i = 0; i < 4 * NV; i++) lte[k * GP::LTE + i] = lti[k * 4 * NV + i];
-        lte[k * GP::LTE + 4 * NV] = 0.0; lte[k * GP::LTE + 4 * NV + 1] = 1.0;
+        for (int i = 0; i < 4 * NV; i++) stg[k * GP::TROW + i] = lti[k * 4 * NV + i];
+        stg[k * GP::TROW + GP::LT_ONE] = 1.0;
+        for (int i = 0; i < S::NY; i++) stg[k * GP::TROW + GP::T_W + i] = W[k * S::NY + i];
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, lte.data()};
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, stg.data()};
     std::vector<double> ws((size_t)B * GR::inst_doubles, 0.0);
     std::vector<double> WeT;                  // kernel layout of the per-instance terminal weights: [nx][B]
     if (We_inst) { WeT.resize((size_t)NX * B); for (int i = 0; i < B; i++) for (int j = 0; j < NX; j++) WeT[(size_t)j * B + i] = We_inst[(size_t)i * NX + j]; }
