@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libnmpc_b200.so")
+LIB_PATH = os.environ.get("NMPC_B200_LIB") or os.path.join(PKG, "libnmpc_b200.so")   # override: kernel experiments (tools/gpu)
 
 # every symbol include/nmpc_b200.h declares
 SYMBOLS = [

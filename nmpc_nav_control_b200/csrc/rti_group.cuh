@@ -137,6 +137,19 @@ NMPC_HD double grp_rsqrt(double d)
 #endif
 }
 
+// running max of |v| (inf-norms): compare + select instead of fmax's NaN-aware sequence; a NaN is ignored here
+// and caught by the mu != mu test of after_B
+NMPC_HD double grp_maxabs(double acc, double v) { v = fabs(v); return v > acc ? v : acc; }
+// pins a pointer in registers (see grp_pin): the running record pointer is advanced, not recomputed
+template <class T>
+NMPC_HD T* grp_pin_ptr(T* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
+
 struct GrpOut {            // per-instance results of K3 (global, indexed by instance of the batch)
     int* qp_status;
     int* qp_iter;
@@ -159,8 +172,8 @@ struct Grp {
     //                     (theta | actual | ref | u); lanes NC.. own the pose components x, y (unit columns)
     //   column/row role : lane j < NX owns state column j of the cost-to-go, of M and K, and row j of
     //                     the dynamics;  lanes UL0.. own the control columns
-    static constexpr int XYL = NC;                        // first lane of the x / y components
-    static constexpr int XY_PER = (G - NC >= 2) ? 1 : 2;  // x and y on two lanes, or both on lane NC
+    static constexpr int XL = NC;                         // lane of the pose component x ...
+    static constexpr int YL = (NC + 1 < G) ? NC + 1 : NC - 1;   // ... and of y (on top of that lane's generic component if G = NC + 1)
     static constexpr int ULN = (G - NX >= NV) ? NV : 1;   // lanes that own control columns (NV / ULN each) ...
     static constexpr int ULB = G > NX ? NX : 0;           // ... starting at this lane
     static constexpr int WL = G > NX ? NX : 0;            // lane that writes the per-stage scalars of the factorisation
@@ -227,8 +240,9 @@ struct Grp {
         double sigmu, mcw;        // copies of the slot's LaneCtl fields the sweeps use (LaneCtl itself lives in the scratch)
         double astep;             // damped step applied by the running B sweep
         int to, wl;               // offset of the warp's stage-table image; lane of the warp
-        const double* We;         // terminal weights of the instance: We[j * ldWe]
-        int ldWe;
+        double We_c, We_xy;       // terminal weight of the lane's generic state component / of its x or y component
+        double* grec;             // record of the stage being processed (advanced stage by stage)
+        const double* tsrc;       // this lane's 16-byte chunk of the stage-table row being prefetched
         // component role (generic components q = r < NC)
         int cq_z, cq_x, cq_y;     // z-order index; state index (-1: control); index into W / y
         int cq_bl, cq_bu;         // lower / upper constraint (NCT: none)
@@ -249,6 +263,7 @@ struct Grp {
         double dxr;               // dx (F) / q_x (Bd) component r
         double du[NV];
         double alpha, S0, S1, S2;
+        double aN, aD;            // ratio test: the binding candidate kept as a fraction aN / aD (aD < 0), divided once per sweep
     };
 
     // lane: lane of the warp; warp: index of the warp's scratch in the shared array
@@ -259,7 +274,7 @@ struct Grp {
         L.to = grp_pin(warp * WARP_D + O_TAB); L.wl = grp_pin(lane);
         L.act = false; L.first = false; L.run = false;
         L.sigmu = 0.0; L.mcw = 1.0;
-        L.astep = 0.0; L.We = nullptr; L.ldWe = 0;
+        L.astep = 0.0; L.We_c = 0.0; L.We_xy = 0.0; L.grec = nullptr; L.tsrc = nullptr;
         // component role: E column q = r -> theta | actual c | ref c | u a
         L.cq_z = 0; L.cq_x = -1; L.cq_y = 0; L.cq_bl = NCT; L.cq_bu = NCT;
         L.cq_i1 = 0; L.cq_i2 = 0; L.cq_k1 = LT_ZERO; L.cq_k2 = LT_ZERO;
@@ -300,9 +315,28 @@ struct Grp {
     enum { SW_B = 0, SW_F = 1, SW_BD = 2, SW_FD = 3 };
 
     // the stage-table row of stage k into image `buf` of the warp (every lane of the warp, running slot or not)
-    NMPC_HD static void issue_tab(const Lane& L, double* sm, const Tables& tb, int k, int buf)
+    NMPC_HD static void issue_tab(const Lane& L, double* sm, const double* src, int buf)
     {
-        if (2 * L.wl < TROW) grp_cp16(sm + L.to + buf * TROW + 2 * L.wl, tb.stg + (size_t)k * TROW + 2 * L.wl);
+        if (2 * L.wl < TROW) grp_cp16(sm + L.to + buf * TROW + 2 * L.wl, src);
+    }
+    // start of a sweep: record / stage-table pointers one stage before the first one (k0), prefetch of k0
+    template <int KIND, int DIR>
+    NMPC_HD static void begin_sweep(Lane& L, double* sm, double* ws, const Tables& tb, int k0)
+    {
+        L.tsrc = grp_pin_ptr(tb.stg + (size_t)k0 * TROW + 2 * L.wl - DIR * TROW);
+        if (L.run) {
+            L.grec = grp_pin_ptr(rec_of(ws, L.li, k0) - DIR * R::NREC);
+            issue<KIND>(L, L.grec + DIR * R::NREC, sm + L.so + O_IN);
+        }
+        issue_tab(L, sm, L.tsrc + DIR * TROW, 0);
+        grp_cp_commit();
+    }
+    // top of a stage: advance to it, wait for its image
+    template <int DIR>
+    NMPC_HD static void begin_stage(Lane& L)
+    {
+        L.grec += DIR * R::NREC; L.tsrc += DIR * TROW;
+        grp_cp_wait_all();
     }
 
     template <int KIND>
@@ -381,25 +415,23 @@ struct Grp {
                 double* scr = sm + L.so;
                 if (L.r < NX) { scr[O_CAR + L.r] = 0.0; scr[O_CAR + NX + L.r] = 0.0; scr[O_CAR + 2 * NX + L.r] = 0.0; scr[O_PV + L.r] = 0.0; }
                 if (L.r < 4) scr[O_CB + 4 * NCT + L.r] = 0.0;
-                issue<SW_B>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
-            issue_tab(L, sm, tb, NSTAGE, 0);
-            grp_cp_commit();
+            begin_sweep<SW_B, -1>(L, sm, ws, tb, NSTAGE);
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
             GRP_PHASE_BEGIN(lanes)
-                grp_cp_wait_all();
+                begin_stage<-1>(L);
             GRP_PHASE_END
             // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
             GRP_PHASE_BEGIN(lanes)
-                if (s < NSTAGE) issue_tab(L, sm, tb, k - 1, buf ^ 1);
+                if (s < NSTAGE) issue_tab(L, sm, L.tsrc - TROW, buf ^ 1);
                 if (!L.run) { grp_cp_commit(); continue; }
                 const double* ltk = sm + L.to + buf * TROW;
                 double* scr = sm + L.so;
-                double* grec = rec_of(ws, L.li, k);
+                double* grec = L.grec;
                 if (s < NSTAGE) issue<SW_B>(L, grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 const double* rec = scr + O_IN + buf * R::NREC;
@@ -422,8 +454,8 @@ struct Grp {
                         const double pm = lam_n * t_n;
                         L.musum += pm;
                         const double rm_n = pm - o.tau_min;
-                        L.nd = fmax(L.nd, fabs(rd_n));
-                        L.nm = fmax(L.nm, fabs(rm_n));
+                        L.nd = grp_maxabs(L.nd, rd_n);
+                        L.nm = grp_maxabs(L.nm, rm_n);
                         const double ti = t_n < o.t_min ? 1.0 / o.t_min : 1.0 / t_n;
                         const double lc = lam_n < o.lam_min ? o.lam_min : lam_n;
                         Gp = ti * lc;
@@ -450,7 +482,7 @@ struct Grp {
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                double* grec = rec_of(ws, L.li, k);
+                double* grec = L.grec;
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
                 double* carn = scr + O_CAR + ((s & 1) ^ 1) * 3 * NX;
@@ -466,7 +498,7 @@ struct Grp {
                     const double v1 = jt_comp(L, e0, e1, e2, k1, k2, car);
                     const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
                     const double v3 = jt_comp(L, e0, e1, e2, k1, k2, scr + O_PV);
-                    const double H = hasU ? tb.dt * ltk[T_W + L.cq_y] : (isx ? L.We[(size_t)L.cq_x * L.ldWe] : 0.0);
+                    const double H = hasU ? tb.dt * ltk[T_W + L.cq_y] : L.We_c;
                     const double qv = rec[R::Q + L.cq_z], z = rec[R::Z + L.cq_z], dz = rec[R::DZ + L.cq_z];
                     const bool haspi = isx && hasX;
                     const double pin = haspi ? rec[R::PI + (isx ? L.cq_x : 0)] : 0.0;
@@ -478,8 +510,8 @@ struct Grp {
                     const double zn = z + a_step * dz;
                     double g = qv + H * zn - pin_n + (v1 + a_step * v2);
                     g += cl[1] + cu[1];
-                    if (has) L.ng = fmax(L.ng, fabs(g));
-                    if (!isx && hasU) L.lru = fmax(L.lru, fabs(r));
+                    if (has) L.ng = grp_maxabs(L.ng, g);
+                    if (!isx && hasU) L.lru = grp_maxabs(L.lru, r);
                     g += cl[2] + cu[2];
                     g += v3;
                     const double dg = H + o.reg_prim + (cl[3] + cu[3]);
@@ -492,34 +524,31 @@ struct Grp {
                     } else {
                         scr[O_GU + L.cq_z] = g; scr[O_DGU + L.cq_z] = dg;
                     }
-                } else if (L.r - XYL < 2) {
+                }
+                if (L.r == XL || L.r == YL) {
                     // pose components x, y: unit columns of J, no bounds
-#pragma unroll
-                    for (int e = 0; e < XY_PER; e++) {
-                        const int j = L.r - XYL + e;
-                        if (j >= 2) continue;
-                        const double v1 = hasU ? car[j] : 0.0, v2 = hasU ? car[NX + j] : 0.0, v3 = hasU ? scr[O_PV + j] : 0.0;
-                        const double H = hasU ? tb.dt * ltk[T_W + j] : L.We[(size_t)j * L.ldWe];
-                        const double qv = rec[R::Q + NU + j], z = rec[R::Z + NU + j], dz = rec[R::DZ + NU + j];
-                        const double pin = hasX ? rec[R::PI + j] : 0.0;
-                        const double r = qv + H * z - pin + v1 + H * dz + v2;
-                        const double pin_n = hasX ? pin + a_step * r : 0.0;
-                        const double zn = z + a_step * dz;
-                        double g = qv + H * zn - pin_n + (v1 + a_step * v2);
-                        if (hasX) L.ng = fmax(L.ng, fabs(g));
-                        g += v3;
-                        grec[R::Z + NU + j] = zn;
-                        grec[R::PI + j] = pin_n;
-                        carn[j] = pin; carn[NX + j] = hasX ? r : 0.0; carn[2 * NX + j] = zn;
-                        scr[O_GX + j] = g; scr[O_DGX + j] = H + o.reg_prim;
-                    }
+                    const int j = L.r == XL ? 0 : 1;
+                    const double v1 = car[j], v2 = car[NX + j], v3 = scr[O_PV + j];      // all zero at the terminal stage
+                    const double H = hasU ? tb.dt * ltk[T_W + j] : L.We_xy;
+                    const double qv = rec[R::Q + NU + j], z = rec[R::Z + NU + j], dz = rec[R::DZ + NU + j];
+                    const double pin = hasX ? rec[R::PI + j] : 0.0;
+                    const double r = qv + H * z - pin + v1 + H * dz + v2;
+                    const double pin_n = hasX ? pin + a_step * r : 0.0;
+                    const double zn = z + a_step * dz;
+                    double g = qv + H * zn - pin_n + (v1 + a_step * v2);
+                    if (hasX) L.ng = grp_maxabs(L.ng, g);
+                    g += v3;
+                    grec[R::Z + NU + j] = zn;
+                    grec[R::PI + j] = pin_n;
+                    carn[j] = pin; carn[NX + j] = hasX ? r : 0.0; carn[2 * NX + j] = zn;
+                    scr[O_GX + j] = g; scr[O_DGX + j] = H + o.reg_prim;
                 }
                 if (hasU && L.r < NX) {
                     // dynamics residual, row r, at the new iterate (recomputed from the record: no exchange)
                     const double rb = jrow(L.r, [&](int c) { return rec[R::Z + c] + a_step * rec[R::DZ + c]; },
                                            [&](int j) { return rec[R::Z + NU + j] + a_step * rec[R::DZ + NU + j]; }, rec + R::E, ltk)
                                       + rec[R::B0 + L.r] - car[2 * NX + L.r];
-                    L.nb = fmax(L.nb, fabs(rb));
+                    L.nb = grp_maxabs(L.nb, rb);
                     scr[O_RB + L.r] = rb;
                     grec[R::RB + L.r] = rb;
                 }
@@ -577,7 +606,7 @@ struct Grp {
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                double* grec = rec_of(ws, L.li, k);
+                double* grec = L.grec;
                 double Luu[NLU];
 #pragma unroll
                 for (int a = 0; a < NV; a++) {
@@ -653,28 +682,26 @@ struct Grp {
     {
         constexpr int KIND = DELTA ? SW_FD : SW_F;
         GRP_PHASE_BEGIN(lanes)
-            L.alpha = -1.0; L.S0 = L.S1 = L.S2 = 0.0; L.dxr = 0.0;
+            L.aN = 1.0; L.aD = -1.0; L.S0 = L.S1 = L.S2 = 0.0; L.dxr = 0.0;
             if (L.run) {
                 double* scr = sm + L.so;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
-                issue<KIND>(L, rec_of(ws, L.li, 0), scr + O_IN);
             }
-            issue_tab(L, sm, tb, 0, 0);
-            grp_cp_commit();
+            begin_sweep<KIND, 1>(L, sm, ws, tb, 0);
         GRP_PHASE_END
 #pragma unroll 1
         for (int k = 0; k <= NSTAGE; k++) {
             const int buf = k & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
             GRP_PHASE_BEGIN(lanes)
-                grp_cp_wait_all();
+                begin_stage<1>(L);
             GRP_PHASE_END
             // ---- F1: prefetch; s_a = lh_a + K_a . dx on the first NV lanes ------------------------------
             GRP_PHASE_BEGIN(lanes)
-                if (k < NSTAGE) issue_tab(L, sm, tb, k + 1, buf ^ 1);
+                if (k < NSTAGE) issue_tab(L, sm, L.tsrc + TROW, buf ^ 1);
                 if (!L.run) { grp_cp_commit(); continue; }
                 double* scr = sm + L.so;
-                if (k < NSTAGE) issue<KIND>(L, rec_of(ws, L.li, k + 1), scr + O_IN + (buf ^ 1) * R::NREC);
+                if (k < NSTAGE) issue<KIND>(L, L.grec + R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 if (!hasU || L.r >= NV) continue;
                 const double* rec = scr + O_IN + buf * R::NREC;
@@ -696,7 +723,7 @@ struct Grp {
                 if (!L.run) continue;
                 double* scr = sm + L.so;
                 const double* rec = scr + O_IN + buf * R::NREC;
-                double* grec = rec_of(ws, L.li, k);
+                double* grec = L.grec;
                 const double* dx = scr + O_CAR + (k & 1) * NX;
                 const double* ltk = sm + L.to + buf * TROW;
 #pragma unroll
@@ -728,8 +755,9 @@ struct Grp {
                         const double dt = sg * dzw - rd;
                         const double dl = -(lam * dt + rm) / t;
                         if (!DELTA) grec[R::MC + c] = dt * dl;
-                        if (L.alpha * dl > lam) L.alpha = lam / dl;
-                        if (L.alpha * dt > t) L.alpha = t / dt;
+                        // ratio test (HPIPM keeps the negated step alpha = aN / aD, aD < 0): alpha * d > n  <=>  aN * d < n * aD
+                        if (L.aN * dl < lam * L.aD) { L.aN = lam; L.aD = dl; }
+                        if (L.aN * dt < t * L.aD) { L.aN = t; L.aD = dt; }
                         L.S0 += lam * t;
                         L.S1 += lam * dt + t * dl;
                         L.S2 += dl * dt;
@@ -755,7 +783,7 @@ struct Grp {
             GRP_PHASE_END
         }
         reduce(lanes, sm, 4, 1,
-               [](const Lane& L, int q) { return q == 0 ? L.alpha : q == 1 ? L.S0 : q == 2 ? L.S1 : L.S2; },
+               [](const Lane& L, int q) { return q == 0 ? L.aN / L.aD : q == 1 ? L.S0 : q == 2 ? L.S1 : L.S2; },
                [](Lane& L, int q, double v) { if (q == 0) L.alpha = v; else if (q == 1) L.S0 = v; else if (q == 2) L.S1 = v; else L.S2 = v; });
     }
 
@@ -768,25 +796,23 @@ struct Grp {
             if (L.run) {
                 double* scr = sm + L.so;
                 if (L.r < NX) scr[O_CAR + L.r] = 0.0;
-                issue<SW_BD>(L, rec_of(ws, L.li, NSTAGE), scr + O_IN);
             }
-            issue_tab(L, sm, tb, NSTAGE, 0);
-            grp_cp_commit();
+            begin_sweep<SW_BD, -1>(L, sm, ws, tb, NSTAGE);
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = NSTAGE - s, buf = s & 1;
             const bool hasU = k < NSTAGE, hasX = k > 0;
             GRP_PHASE_BEGIN(lanes)
-                grp_cp_wait_all();
+                begin_stage<-1>(L);
             GRP_PHASE_END
             // ---- D1: q = J' dp + complementarity terms, one component per lane -----------------------
             GRP_PHASE_BEGIN(lanes)
-                if (s < NSTAGE) issue_tab(L, sm, tb, k - 1, buf ^ 1);
+                if (s < NSTAGE) issue_tab(L, sm, L.tsrc - TROW, buf ^ 1);
                 if (!L.run) { grp_cp_commit(); continue; }
                 const double* ltk = sm + L.to + buf * TROW;
                 double* scr = sm + L.so;
-                if (s < NSTAGE) issue<SW_BD>(L, rec_of(ws, L.li, k - 1), scr + O_IN + (buf ^ 1) * R::NREC);
+                if (s < NSTAGE) issue<SW_BD>(L, L.grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
                 grp_cp_commit();
                 const double* rec = scr + O_IN + buf * R::NREC;
                 const double* dp = scr + O_CAR + (s & 1) * NX;
@@ -803,12 +829,10 @@ struct Grp {
                         qv += (mcw * rec[R::MC + L.cq_bl] - L.sigmu) / tl - (mcw * rec[R::MC + L.cq_bu] - L.sigmu) / tu;
                     }
                     if (isx) scr[O_GX + L.cq_x] = qv; else scr[O_GU + L.cq_z] = qv;
-                } else if (L.r - XYL < 2) {
-#pragma unroll
-                    for (int e = 0; e < XY_PER; e++) {
-                        const int j = L.r - XYL + e;
-                        if (j < 2) scr[O_GX + j] = hasU ? dp[j] : 0.0;
-                    }
+                }
+                if (L.r == XL || L.r == YL) {
+                    const int j = L.r == XL ? 0 : 1;
+                    scr[O_GX + j] = dp[j];            // zero at the terminal stage
                 }
             GRP_PHASE_END
             // ---- D2: lh = L^-1 q_u (every lane), dp = q_x - K' lh -------------------------------------
@@ -826,7 +850,7 @@ struct Grp {
                         L.lh[a] = sacc * rec[R::LUU + a * (a + 1) / 2 + a];
                     }
                     if (L.r == WL) {
-                        double* grec = rec_of(ws, L.li, k);
+                        double* grec = L.grec;
 #pragma unroll
                         for (int a = 0; a < NV; a++) grec[R::LHD + a] = L.lh[a];
                     }
@@ -863,7 +887,10 @@ struct Grp {
                     const int idx = *reinterpret_cast<const int*>(sm + L.so + O_RED);
                     if (idx < n) {
                         L.act = true; L.first = true; L.li = idx;
-                        if (We_inst) { L.We = We_inst + i0 + idx; L.ldWe = ldWe; } else { L.We = tb.We; L.ldWe = 1; }
+                        const double* wp = We_inst ? We_inst + i0 + idx : tb.We;
+                        const size_t wl = We_inst ? (size_t)ldWe : 1;
+                        L.We_c = (L.r < NC && L.cq_x >= 0) ? wp[(size_t)L.cq_x * wl] : 0.0;
+                        L.We_xy = L.r == XL ? wp[0] : (L.r == YL ? wp[wl] : 0.0);
                         if (L.r == 0) CTL(L).init(true);
                     }
                 } else if (L.r == 0) sm[L.so + O_AST] = S::before_B(CTL(L));
