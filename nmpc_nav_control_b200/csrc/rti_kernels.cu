@@ -223,7 +223,13 @@ k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const
     }
 }
 
-constexpr int GRP_WARPS = 4;           // warps per CTA of the group kernel
+#ifndef NMPC_GRP_WARPS
+#define NMPC_GRP_WARPS 4
+#endif
+#ifndef NMPC_GRP_MINB
+#define NMPC_GRP_MINB 3
+#endif
+constexpr int GRP_WARPS = NMPC_GRP_WARPS;           // warps per CTA of the group kernel
 
 // K3, group path: persistent warps, each running the whole interior-point loop of 32/G instances at a
 // time and refilling converged slots from the queue *next (instances [0, n) of the chunk).
@@ -800,7 +806,7 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
         CK(cudaEventRecord(ev[1], st));
         const int G = s->grp_G;
         if constexpr (S::NV == 2) {
-            if (G == 8) rc = launch_group<M, 8, 3>(s, i0, n, tb, d_We, B, o, out, st);
+            if (G == 8) rc = launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, B, o, out, st);
             else if (G == 16) rc = launch_group<M, 16, 3>(s, i0, n, tb, d_We, B, o, out, st);
             else rc = launch_group<M, 32, 3>(s, i0, n, tb, d_We, B, o, out, st);
         } else {

@@ -1,5 +1,7 @@
-"""CPU check of the CUDA solver's per-lane arithmetic: rti_core.cuh compiled by g++ as a lane-by-lane
-emulation (tests/host_emul) against the oracle.  The structured Riccati / delta-corrector path of
+"""CPU check of the CUDA solver's arithmetic against the oracle, through tests/host_emul (the kernel headers
+compiled by g++): the lane-group K3 that ships by default (rti_group.cuh; an emulated warp of 32 lanes runs
+its bulk-synchronous phases lane by lane, G lanes per instance) and the per-lane K3 (rti_core.cuh, the
+NMPC_K3=sweep path).  The structured Riccati / delta-corrector path of
 the kernels is a different factorisation of the same Newton systems as the oracle's dense
 square-root Riccati, so agreement is to rounding, not bit-exact; iteration counts must be equal."""
 import numpy as np
@@ -9,18 +11,35 @@ import emul
 from helpers import instances, oracle_solve, parity_report
 
 
+GROUP = {"diff": 8, "tric": 8, "omni4": 16}     # lanes per instance of the shipped configuration
+
+
+@pytest.mark.parametrize("group", [True, False])
 @pytest.mark.parametrize("name,B,start", [("diff", 192, 0), ("omni4", 64, 300), ("tric", 128, 77)])
-def test_cold_step_matches_oracle(oracle_mod, name, B, start):
+def test_cold_step_matches_oracle(oracle_mod, name, B, start, group):
     spec, x0, yref, _ = instances(name, start, B)
     ref = oracle_solve(oracle_mod, name, x0, yref)
-    out = emul.emul_rti(name, x0, yref)
+    out = emul.emul_rti(name, x0, yref, group=GROUP[name] if group else 0)
     assert (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["x"], ref["x"])[0] == 0
     assert parity_report(out["u"], ref["u"])[0] == 0
 
 
+def test_group_slot_refill_and_other_group_sizes(oracle_mod):
+    """more instances than slots of the emulated warps (slots are refilled from the queue as instances converge,
+    ragged last round), and the wider groups (16 / 32 lanes per instance) of the same template"""
+    for name, G, B in (("diff", 8, 45), ("diff", 16, 21), ("tric", 32, 7), ("omni4", 32, 5)):
+        spec, x0, yref, _ = instances(name, 2500, B)
+        ref = oracle_solve(oracle_mod, name, x0, yref)
+        out = emul.emul_rti(name, x0, yref, group=G)
+        assert (out["qp_status"] == 0).all()
+        assert (out["qp_iter"] == ref["qp_iter"]).all(), (name, G)
+        assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, (name, G)
+
+
+@pytest.mark.parametrize("group", [True, False])
 @pytest.mark.parametrize("name", ["diff", "omni4", "tric"])
-def test_warm_steps_and_pose_only_yref(oracle_mod, name):
+def test_warm_steps_and_pose_only_yref(oracle_mod, name, group):
     """three consecutive RTI steps (iterate carried over, x0 <- x1), pose-only yref in the kernel path"""
     B = 48
     spec, x0, yref3, _ = instances(name, 9000, B, pose_only=True)
@@ -29,7 +48,7 @@ def test_warm_steps_and_pose_only_yref(oracle_mod, name):
     x0r, x0e = x0.copy(), x0.copy()
     for step in range(3):
         ref = oracle_solve(oracle_mod, name, x0r, yfull, x=xr, u=ur)
-        out = emul.emul_rti(name, x0e, yref3, x=xe, u=ue)
+        out = emul.emul_rti(name, x0e, yref3, x=xe, u=ue, group=GROUP[name] if group else 0)
         assert (out["qp_iter"] == ref["qp_iter"]).all(), step
         lr = ref["lin_res"]
         assert (lr > 1e-10).sum() <= 2, step          # ill-conditioned QPs are the exception
@@ -38,16 +57,18 @@ def test_warm_steps_and_pose_only_yref(oracle_mod, name):
         x0r, x0e = xr[:, 1].copy(), xe[:, 1].copy()
 
 
-def test_diff_per_instance_terminal_weight(oracle_mod):
+@pytest.mark.parametrize("group", [8, 0])
+def test_diff_per_instance_terminal_weight(oracle_mod, group):
     B = 64
     spec, x0, yref, We = instances("diff", 100, B, terminal_hack=True)
     ref = oracle_solve(oracle_mod, "diff", x0, yref, We=We)
-    out = emul.emul_rti("diff", x0, yref, We=We)
+    out = emul.emul_rti("diff", x0, yref, We=We, group=group)
     assert (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["u"], ref["u"])[0] == 0
 
 
-def test_nondefault_tables(oracle_mod):
+@pytest.mark.parametrize("group", [True, False])
+def test_nondefault_tables(oracle_mod, group):
     """stage-varying weights / bounds / parameters set through the table setters"""
     rng = np.random.default_rng(5)
     for name in ("diff", "tric", "omni4"):
@@ -62,6 +83,6 @@ def test_nondefault_tables(oracle_mod):
         tb["p"] = tb["p"] * (1.0 + 0.05 * rng.random(tb["p"].shape))
         yref[:, :, 3:] = 0.1 * rng.standard_normal(yref[:, :, 3:].shape)       # full-width yref
         ref = oracle_solve(oracle_mod, name, x0, yref, tables=tb)
-        out = emul.emul_rti(name, x0, yref, tables=tb)
+        out = emul.emul_rti(name, x0, yref, tables=tb, group=GROUP[name] if group else 0)
         assert (out["qp_iter"] == ref["qp_iter"]).all(), name
         assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, name

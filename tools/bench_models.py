@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the contract bench line): device-resident throughput of the three models at
+several batch sizes, and the batch-1 latency through the host-buffer C ABI (what the ROS drop-in would see).
+    python tools/bench_models.py [--latency-calls 1000]
+Prints one JSON object per line."""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from nmpc_nav_control_b200 import synth
+from nmpc_nav_control_b200.problem import MODELS
+from nmpc_nav_control_b200.solver import BatchedRtiSolver
+
+
+def throughput(name, B, steps=3, warm=2):
+    spec = MODELS[name]
+    dev = torch.device("cuda", 0)
+    inst = synth.make_instances(spec, 0, B, device=dev, pose_only=True)
+    x0 = inst["x0"].t().contiguous(); yref = inst["yref"].permute(1, 2, 0).contiguous()
+    s = BatchedRtiSolver(spec, B)
+    out = dict(status=torch.empty(B, dtype=torch.int32, device=dev), qp_iter=torch.empty(B, dtype=torch.int32, device=dev))
+    for _ in range(warm):
+        s.reset_async(); s.solve_device(x0, yref, out=out)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s.reset_async(); s.solve_device(x0, yref, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t = s.last_timing()
+    r = dict(kind="throughput", model=name, batch=B, ms_per_step=ms, solves_per_s=B / ms * 1e3,
+             mean_qp_iter=float(out["qp_iter"].double().mean()), max_qp_iter=int(out["qp_iter"].max()),
+             status_nonzero=int((out["status"] != 0).sum()), kernel_ms=t)
+    s.close()
+    return r
+
+
+def latency(name, calls):
+    spec = MODELS[name]
+    inst = synth.make_instances(spec, 0, 1, pose_only=True)
+    x0 = inst["x0"].numpy().copy(); yref = inst["yref"].numpy().copy()
+    s = BatchedRtiSolver(spec, 1)
+    s.reset()
+    out = None
+    for _ in range(100):
+        out = s.solve_host(x0, yref, out=out)
+    ts = []
+    for _ in range(calls):
+        s.reset()                      # cold iterate: the worst case of a tick (a warm tick needs fewer QP iterations)
+        t0 = time.perf_counter()
+        out = s.solve_host(x0, yref, out=out)
+        ts.append((time.perf_counter() - t0) * 1e6)
+    ts = np.array(ts)
+    r = dict(kind="latency_batch1", model=name, calls=calls, p50_us=float(np.percentile(ts, 50)), p95_us=float(np.percentile(ts, 95)),
+             p99_us=float(np.percentile(ts, 99)), qp_iter=int(out["qp_iter"][0]), api="nmpc_rti_solve_host (cold iterate)")
+    s.close()
+    return r
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--latency-calls", type=int, default=1000)
+    ap.add_argument("--batches", default="diff:65536,diff:131072,tric:65536,omni4:65536,omni4:262144")
+    a = ap.parse_args()
+    for item in a.batches.split(","):
+        if not item:
+            continue
+        n, b = item.split(":")
+        print(json.dumps(throughput(n, int(b))), flush=True)
+    for n in ("diff", "omni4", "tric"):
+        print(json.dumps(latency(n, a.latency_calls)), flush=True)
