@@ -156,6 +156,14 @@ struct GrpOut {            // per-instance results of K3 (global, indexed by ins
     double* stats;         // [8][B] or null
     int B;                 // leading dimension of stats
 };
+// hand-over from the per-sweep kernels (hybrid schedule): the queue holds *n_dev records, record q belongs to
+// instance list[q] of the chunk, is in the middle of an iteration (factorised, predictor not yet run) and
+// continues with the control block ctl[q] (an array of Rti<M>::LaneCtl).  All null = every instance from the cold start.
+struct GrpResume {
+    const int* n_dev;
+    const int* list;
+    const void* ctl;
+};
 
 template <class M, int G_>
 struct Grp {
@@ -237,6 +245,8 @@ struct Grp {
         int r, so;                // role index in the group; offset (doubles) of the slot's scratch in the shared array
         int li;                   // instance (index into the chunk) of the slot, -1 = none
         bool act, first, run;     // slot has an instance / its next B sweep is the first / takes part in the current sweep
+        bool skipB;               // resumed instance: joins the loop at the predictor, skipping the factorising sweep once
+        int gi;                   // instance of the chunk the slot's record belongs to (= li unless resumed)
         double sigmu, mcw;        // copies of the slot's LaneCtl fields the sweeps use (LaneCtl itself lives in the scratch)
         double astep;             // damped step applied by the running B sweep
         int to, wl;               // offset of the warp's stage-table image; lane of the warp
@@ -272,7 +282,7 @@ struct Grp {
         const int r = grp_pin(lane % G);
         L.r = r; L.so = grp_pin(warp * WARP_D + (lane / G) * SLOT_D); L.li = -1;
         L.to = grp_pin(warp * WARP_D + O_TAB); L.wl = grp_pin(lane);
-        L.act = false; L.first = false; L.run = false;
+        L.act = false; L.first = false; L.run = false; L.skipB = false; L.gi = -1;
         L.sigmu = 0.0; L.mcw = 1.0;
         L.astep = 0.0; L.We_c = 0.0; L.We_xy = 0.0; L.grec = nullptr; L.tsrc = nullptr;
         // component role: E column q = r -> theta | actual c | ref c | u a
@@ -300,6 +310,36 @@ struct Grp {
         L.cq_z = grp_pin(L.cq_z); L.cq_x = grp_pin(L.cq_x); L.cq_y = grp_pin(L.cq_y); L.cq_bl = grp_pin(L.cq_bl); L.cq_bu = grp_pin(L.cq_bu);
         L.cq_i1 = grp_pin(L.cq_i1); L.cq_i2 = grp_pin(L.cq_i2); L.cq_k1 = grp_pin(L.cq_k1); L.cq_k2 = grp_pin(L.cq_k2);
         L.ct_z = grp_pin(L.ct_z); L.ct_x = grp_pin(L.ct_x); L.ct_u = grp_pin(L.ct_u);
+    }
+
+    // hand-over from the per-sweep path: stage k of one instance from its tile (Rec<NV>, lane-resolved pointer,
+    // field stride LANES) into a group record.  State right after a factorising sweep: QP data, iterate,
+    // factorisation (the steps DZ / DZA / MC / LHD are rewritten before they are read again).
+    NMPC_HD static void tile_to_record(const double* tl, int k, double* rec)
+    {
+        using T = typename S::R;
+        const double* lin = tl + T::OFF_LIN + (size_t)k * T::NF_LIN * LANES;
+        const double* it = tl + T::OFF_IT + (size_t)k * T::NF_IT * LANES;
+        const double* fa = tl + T::OFF_FA + (size_t)k * T::NF_FA * LANES;
+        for (int i = 0; i < NZ; i++) rec[R::Q + i] = lin[(T::Q + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::B0 + i] = lin[(T::B0 + i) * LANES];
+        for (int i = 0; i < NB2; i++) { rec[R::DLB + i] = lin[(T::DLB + i) * LANES]; rec[R::DUB + i] = lin[(T::DUB + i) * LANES]; }
+        for (int i = 0; i < 3 * NC; i++) rec[R::E + i] = lin[(T::E + i) * LANES];
+        for (int i = 0; i < NLU; i++) rec[R::LUU + i] = fa[(T::LUU + i) * LANES];
+        for (int i = 0; i < NV * NX; i++) rec[R::KH + i] = fa[(T::KH + i) * LANES];
+        for (int i = 0; i < NV; i++) rec[R::LH + i] = fa[(T::LH + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::RB + i] = fa[(T::RB + i) * LANES];
+        for (int i = 0; i < 2 * NB2; i++) { rec[R::T + i] = it[(T::T + i) * LANES]; rec[R::LAM + i] = it[(T::LAM + i) * LANES]; }
+        for (int i = 0; i < NZ; i++) rec[R::Z + i] = it[(T::Z + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::PI + i] = it[(T::PI + i) * LANES];
+        // padding and the step fields stay defined
+        if ((3 * NC) & 1) rec[R::E + 3 * NC] = 0.0;
+        if (NLU & 1) rec[R::LUU + NLU] = 0.0;
+        if (NX & 1) { rec[R::RB + NX] = 0.0; rec[R::PI + NX] = 0.0; }
+        if (NZ & 1) { rec[R::Z + NZ] = 0.0; rec[R::DZ + NZ] = 0.0; rec[R::DZA + NZ] = 0.0; }
+        for (int i = 0; i < NV; i++) rec[R::LHD + i] = 0.0;
+        for (int i = 0; i < NZ; i++) { rec[R::DZ + i] = 0.0; rec[R::DZA + i] = 0.0; }
+        for (int i = 0; i < 2 * NB2; i++) rec[R::MC + i] = 0.0;
     }
 
     NMPC_HD static double* rec_of(double* ws, int li, int k) { return ws + (size_t)li * R::inst_doubles + (size_t)k * R::NREC; }
@@ -870,8 +910,9 @@ struct Grp {
     // work queue `next` (instances [0, n) of the chunk) at every iteration boundary
     // =========================================================================================
     NMPC_HD static void run_warp(Lane* lanes, double* sm, double* ws, int i0, int n, int* next, const Tables& tb,
-                                 const double* We_inst, int ldWe, const IpmOpts& o, const GrpOut& out)
+                                 const double* We_inst, int ldWe, const IpmOpts& o, const GrpOut& out, const GrpResume& rs)
     {
+        if (rs.n_dev) n = *rs.n_dev;
 #define CTL(L) (*reinterpret_cast<LaneCtl*>(sm + (L).so + O_CTL))
 #pragma unroll 1
         for (;;) {
@@ -886,34 +927,36 @@ struct Grp {
                 if (!L.act) {
                     const int idx = *reinterpret_cast<const int*>(sm + L.so + O_RED);
                     if (idx < n) {
-                        L.act = true; L.first = true; L.li = idx;
-                        const double* wp = We_inst ? We_inst + i0 + idx : tb.We;
+                        L.act = true; L.li = idx;
+                        L.first = rs.list == nullptr; L.skipB = !L.first;
+                        L.gi = rs.list ? rs.list[idx] : idx;
+                        const double* wp = We_inst ? We_inst + i0 + L.gi : tb.We;
                         const size_t wl = We_inst ? (size_t)ldWe : 1;
                         L.We_c = (L.r < NC && L.cq_x >= 0) ? wp[(size_t)L.cq_x * wl] : 0.0;
                         L.We_xy = L.r == XL ? wp[0] : (L.r == YL ? wp[wl] : 0.0);
-                        if (L.r == 0) CTL(L).init(true);
+                        if (L.r == 0) { if (rs.list) CTL(L) = reinterpret_cast<const LaneCtl*>(rs.ctl)[idx]; else CTL(L).init(true); }
                     }
                 } else if (L.r == 0) sm[L.so + O_AST] = S::before_B(CTL(L));
             GRP_PHASE_END
             GRP_PHASE_BEGIN(lanes)
-                L.run = L.act;
+                L.run = L.act && !L.skipB;
                 L.astep = 0.0;
                 if (L.act) {
-                    if (!L.first) L.astep = sm[L.so + O_AST];
+                    if (!L.first && !L.skipB) L.astep = sm[L.so + O_AST];
                     L.sigmu = CTL(L).sigmu; L.mcw = CTL(L).mcw;
                 }
             GRP_PHASE_END
             if (!warp_any(lanes, [](const Lane& L) { return L.act; })) break;
 
-            sweep_B(lanes, sm, ws, tb, o);
+            if (warp_any(lanes, [](const Lane& L) { return L.run; })) sweep_B(lanes, sm, ws, tb, o);
             GRP_PHASE_BEGIN(lanes)
-                if (!L.act || L.r != 0) continue;
+                if (!L.run || L.r != 0) continue;
                 LaneCtl& c = CTL(L);
                 typename S::CarryB cy;
                 cy.ng = L.ng; cy.nb = L.nb; cy.nd = L.nd; cy.nm = L.nm; cy.musum = L.musum; cy.lru = L.lru;
                 S::after_B(c, cy, o, L.first);
                 if (c.done) {
-                    const int i = i0 + L.li;
+                    const int i = i0 + L.gi;
                     out.qp_status[i] = c.status;
                     out.qp_iter[i] = c.iter;
                     if (out.stats) {
@@ -927,7 +970,8 @@ struct Grp {
                 }
             GRP_PHASE_END
             GRP_PHASE_BEGIN(lanes)
-                if (L.act) { L.first = false; if (CTL(L).done) L.act = false; }
+                if (L.run) { L.first = false; if (CTL(L).done) L.act = false; }
+                L.skipB = false;
                 L.run = L.act;
             GRP_PHASE_END
             if (!warp_any(lanes, [](const Lane& L) { return L.act; })) continue;

@@ -141,11 +141,11 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
 template <class M, int KIND>
 __global__ void __launch_bounds__(LANES * SW_TILES, KIND == 5 ? 8 : 4)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
-        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out)
+        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min)
 {
     using S = Rti<M>;
     using R = typename S::R;
-    if (KIND != S::SW_B_FIRST && *gate == 0) return;
+    if (KIND != S::SW_B_FIRST && *gate < gate_min) return;     // gate_min = 1: run while any lane iterates
     extern __shared__ double scratch_buf[];       // B sweeps: CarryB::SC_N columns of NMPC_SCRATCH_STRIDE doubles
     double* scratch = scratch_buf;
     const int li = blockIdx.x * (LANES * SW_TILES) + threadIdx.x;
@@ -236,13 +236,13 @@ constexpr int GRP_WARPS = NMPC_GRP_WARPS;           // warps per CTA of the grou
 template <class M, int G, int MINB>
 __global__ void __launch_bounds__(GRP_WARPS * 32, MINB)
 k_ipm_group(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldWe, IpmOpts o, double* __restrict__ ws,
-            int* __restrict__ next, GrpOut out)
+            int* __restrict__ next, GrpOut out, GrpResume rs)
 {
     using GP = Grp<M, G>;
     extern __shared__ __align__(16) double grp_sm[];
     typename GP::Lane L;
     GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
-    GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out);
+    GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out, rs);
 }
 
 // K4 from the group layout
@@ -267,6 +267,74 @@ k_step_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __
         for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
     }
     S::template step_stage<GR, 1>(k, rec, xb, xk, uk);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { x[((size_t)k * S::NX + j) * ld + i] = xk[j]; bad |= (xk[j] != xk[j]); }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) u[((size_t)k * S::NU + c) * ld + i] = uk[c];
+    }
+    if (bad) atomicMax(&status[i], NMPC_NAN_DETECTED);
+}
+
+// ---- hybrid schedule: hand-over of the instances the per-sweep kernels did not finish ----------------------
+// compaction: unfinished instance li -> record q = map[li] of the group workspace, list[q] = li, its control block
+template <class M>
+__global__ void k_handover_compact(int nchunk, int ldc, const double* __restrict__ ctl_d, const int* __restrict__ ctl_i,
+                                   int* __restrict__ nres, int* __restrict__ list, int* __restrict__ map, void* __restrict__ ctl_out)
+{
+    using S = Rti<M>;
+    static_assert(sizeof(typename S::LaneCtl) <= 128, "d_ctl_g is sized 128 bytes per instance");
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    int q = -1;
+    if (ctl_i[li] == 0) {                              // row 0 = done
+        q = atomicAdd(nres, 1);
+        list[q] = li;
+        typename S::LaneCtl c;
+        ctl_load<S>(c, ctl_d, ctl_i, ldc, li);
+        reinterpret_cast<typename S::LaneCtl*>(ctl_out)[q] = c;
+    }
+    map[li] = q;
+}
+// state of the unfinished instances from the tile layout into their group records; grid (instances, stages)
+template <class M, int G>
+__global__ void __launch_bounds__(128)
+k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp)
+{
+    using GP = Grp<M, G>;
+    using R = typename Rti<M>::R;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (li >= nchunk) return;
+    const int q = map[li];
+    if (q < 0) return;
+    GP::tile_to_record(ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES), k, GP::rec_of(ws_grp, q, k));
+}
+// K4 for the hybrid schedule: the step of an instance comes from its tile or, if it was handed over, from its group record
+template <class M>
+__global__ void __launch_bounds__(LIN_BLOCK)
+k_step_h(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __restrict__ x, double* __restrict__ u, int ld,
+         const double* __restrict__ ws_tile, const double* __restrict__ ws_grp, const int* __restrict__ map,
+         const int* __restrict__ qp_status, int* __restrict__ status)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    using GR = GRec<S::NV>;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= nchunk) return;
+    const int i = i0 + li, k = blockIdx.y;
+    const int qs = qp_status[i];
+    if (qs != 0 && qs != 1) { if (k == 0) status[i] = NMPC_QP_FAILURE; return; }
+    double xk[S::NX], uk[S::NU], xb[S::NX];
+#pragma unroll
+    for (int j = 0; j < S::NX; j++) { xk[j] = x[((size_t)k * S::NX + j) * ld + i]; xb[j] = (k == 0) ? x0bar[(size_t)j * B + i] : 0.0; }
+    if (k < NSTAGE) {
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
+    }
+    const int q = map[li];
+    if (q >= 0) S::template step_stage<GR, 1>(k, ws_grp + (size_t)q * GR::inst_doubles + (size_t)k * GR::NREC, xb, xk, uk);
+    else S::step_stage(k, ws_tile + (size_t)(li / LANES) * R::tile_doubles + R::OFF_IT + (size_t)k * R::NF_IT * LANES + (li % LANES), xb, xk, uk);
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < S::NX; j++) { x[((size_t)k * S::NX + j) * ld + i] = xk[j]; bad |= (xk[j] != xk[j]); }
@@ -423,7 +491,12 @@ static const ModelInfo g_models[3] = {
 
 struct nmpc_solver {
     int model, cap, device, chunk;
-    int k3_group = 1;            // 1: lane-group persistent K3 (rti_group.cuh); 0: per-sweep kernels (rti_core.cuh)
+    int k3_group = 2;            // K3 schedule: 0 per-sweep kernels (rti_core.cuh), 1 lane-group persistent kernel (rti_group.cuh),
+                                 // 2 hybrid: per-sweep kernels while most instances iterate, then the group kernel for the rest
+    double *d_ws_g = nullptr;    // group workspace (schedules 1, 2)
+    int *d_list = nullptr, *d_map = nullptr;
+    void* d_ctl_g = nullptr;
+    int hyb_kmax = 12; double hyb_frac = 0.5;
     int grp_G = 0, grp_blocks = 0;
     size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
@@ -528,24 +601,31 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     const int cap_pad = (max_batch + LANES - 1) / LANES * LANES;
     s->chunk = chunk < cap_pad ? chunk : cap_pad;
     s->tile_doubles = tile_doubles_of(model);
-    if (const char* e = getenv("NMPC_K3")) s->k3_group = strcmp(e, "sweep") != 0;
+    if (const char* e = getenv("NMPC_K3")) s->k3_group = !strcmp(e, "sweep") ? 0 : !strcmp(e, "group") ? 1 : 2;
+    if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
+    if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
     s->grp_G = (model == 1) ? 16 : 8;
     if (const char* e = getenv("NMPC_GRP_G")) { int v = atoi(e); if ((v == 8 && model != 1) || v == 16 || v == 32) s->grp_G = v; }
     {
-        const size_t per_group = (model == 1) ? GRec<4>::inst_doubles : GRec<2>::inst_doubles;
-        const size_t per_sweep = s->tile_doubles / LANES;
-        s->ws_doubles_per_inst = s->k3_group ? per_group : per_sweep;
+        s->ws_doubles_per_inst = s->tile_doubles / LANES;
     }
     cudaError_t e;
 #define CKC(call) do { e = (call); if (e != cudaSuccess) { set_err(NMPC_E_CUDA, #call, e); nmpc_destroy(s); return NMPC_E_CUDA; } } while (0)
     CKC(cudaMalloc(&s->d_tab, s->tab_doubles * sizeof(double)));
     CKC(cudaMalloc(&s->d_x, (size_t)max_batch * (n + 1) * nx * sizeof(double)));
     CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
-    CKC(cudaMalloc(&s->d_ws, (size_t)s->chunk * s->ws_doubles_per_inst * sizeof(double)));
+    if (s->k3_group != 1) CKC(cudaMalloc(&s->d_ws, (size_t)s->chunk * s->ws_doubles_per_inst * sizeof(double)));
+    if (s->k3_group != 0) {
+        const size_t per_group = (model == 1) ? GRec<4>::inst_doubles : GRec<2>::inst_doubles;
+        CKC(cudaMalloc(&s->d_ws_g, (size_t)s->chunk * per_group * sizeof(double)));
+        CKC(cudaMalloc(&s->d_list, (size_t)s->chunk * sizeof(int)));
+        CKC(cudaMalloc(&s->d_map, (size_t)s->chunk * sizeof(int)));
+        CKC(cudaMalloc(&s->d_ctl_g, (size_t)s->chunk * 128));
+    }
     CKC(cudaMalloc(&s->d_qp_status, (size_t)max_batch * sizeof(int)));
     CKC(cudaMalloc(&s->d_ctl_d, (size_t)NCTL_D * s->chunk * sizeof(double)));
     CKC(cudaMalloc(&s->d_ctl_i, (size_t)NCTL_I * s->chunk * sizeof(int)));
-    s->cnt_cap = 1002;
+    s->cnt_cap = 1008;      // act[0..iter_max] of the sweep schedule (iter_max <= 1000), then the hand-over count and the group queue
     CKC(cudaMalloc(&s->d_cnt, (size_t)s->cnt_cap * sizeof(int)));
     CKC(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&s->ev_total[0])); CKC(cudaEventCreate(&s->ev_total[1]));
@@ -568,6 +648,7 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
     cudaSetDevice(s->device);
     cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
     cudaFree(s->d_ctl_d); cudaFree(s->d_ctl_i); cudaFree(s->d_cnt);
+    cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
     cudaFree(s->d_status); cudaFree(s->d_iter); cudaFree(s->d_stats);
     for (auto e : s->ev) cudaEventDestroy(e);
@@ -693,6 +774,52 @@ static int ensure_events(nmpc_solver* s, int nchunks)
     return 0;
 }
 
+// ---- group path: one persistent launch per chunk ------------------------------------------------
+template <class M, int G, int MINB>
+static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
+                        const GrpOut& out, const GrpResume& rs, cudaStream_t st)
+{
+    using GP = Grp<M, G>;
+    const size_t smem = (size_t)GRP_WARPS * GP::WARP_D * sizeof(double);
+    static int blocks_per_sm = 0;          // per template instantiation
+    if (!blocks_per_sm) {
+        CK(cudaFuncSetAttribute(k_ipm_group<M, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ipm_group<M, G, MINB>, GRP_WARPS * 32, smem));
+        if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_group does not fit on an SM");
+        if (const char* e = getenv("NMPC_GRP_BPS")) { int v = atoi(e); if (v >= 1 && v < nb) nb = v; }
+        blocks_per_sm = nb;
+    }
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
+    const int per_block = GRP_WARPS * GP::NSLOT;
+    int blocks = nsm * blocks_per_sm;
+    const int need = (n + per_block - 1) / per_block;        // n: upper bound of the queue length (resume: the chunk)
+    if (blocks > need) blocks = need;
+    s->grp_blocks = blocks;
+    int* queue = s->d_cnt + s->cnt_cap - 1;
+    CK(cudaMemsetAsync(queue, 0, sizeof(int), st));
+    k_ipm_group<M, G, MINB><<<blocks, GRP_WARPS * 32, smem, st>>>(i0, n, tb, d_We, ldWe, o, s->d_ws_g, queue, out, rs);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class M>
+static int launch_group_any(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
+                            const GrpOut& out, const GrpResume& rs, cudaStream_t st)
+{
+    using S = Rti<M>;
+    const int G = s->grp_G;
+    if constexpr (S::NV == 2) {
+        if (G == 8) return launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
+        if (G == 16) return launch_group<M, 16, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
+        return launch_group<M, 32, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
+    } else {
+        if (G == 32) return launch_group<M, 32, 2>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
+        return launch_group<M, 16, 2>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
+    }
+}
+
 template <class M>
 static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
                           double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st)
@@ -726,18 +853,40 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 attr_set = true;
             }
             CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)s->cnt_cap * sizeof(int), st));
-            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act);
+            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 1);
             s->last_launches++;
-            for (int it = 0; it < o.iter_max; it++) {
-                k_sweep<M, S::SW_FDF><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr);
-                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1);
+            // hybrid schedule: the lockstep sweeps run while at least gate_min instances iterate (a sweep costs the
+            // same whether 100% or 10% of the lanes are active), at most kmax iterations; whatever is unfinished is
+            // handed to the persistent lane-group kernel, which has no lockstep between instances
+            const bool hybrid = s->k3_group == 2;
+            const int kmax = hybrid ? (s->hyb_kmax < o.iter_max ? s->hyb_kmax : o.iter_max) : o.iter_max;
+            int gate_min = 1;
+            if (hybrid) { gate_min = (int)(s->hyb_frac * n); if (gate_min < 1) gate_min = 1; }
+            for (int it = 0; it < kmax; it++) {
+                k_sweep<M, S::SW_FDF><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, gate_min);
+                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, gate_min);
                 s->last_launches += 2;
             }
             k_ipm_finish<<<(n + 255) / 256, 256, 0, st>>>(B, i0, n, ldc, s->d_ctl_d, s->d_ctl_i, s->d_qp_status, d_qp_iter, d_stats);
             s->last_launches++;
+            if (hybrid) {
+                int* nres = s->d_cnt + s->cnt_cap - 2;
+                k_handover_compact<M><<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, nres, s->d_list, s->d_map, s->d_ctl_g);
+                dim3 gc((n + 127) / 128, NSTAGE + 1);
+                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
+                rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nres, s->d_list, s->d_ctl_g}, st);
+                if (rc) return rc;
+                s->last_launches += 3;
+            }
         }
         CK(cudaEventRecord(ev[2], st));
-        k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
+        if (s->k3_group == 2)
+            k_step_h<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_ws_g, s->d_map, s->d_qp_status, d_status);
+        else
+            k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
         CK(cudaEventRecord(ev[3], st));
         s->last_launches += 3;
     }
@@ -745,35 +894,6 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
     return 0;
 }
 
-
-// ---- group path: one persistent launch per chunk ------------------------------------------------
-template <class M, int G, int MINB>
-static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
-                        const GrpOut& out, cudaStream_t st)
-{
-    using GP = Grp<M, G>;
-    const size_t smem = (size_t)GRP_WARPS * GP::WARP_D * sizeof(double);
-    static int blocks_per_sm = 0;          // per template instantiation
-    if (!blocks_per_sm) {
-        CK(cudaFuncSetAttribute(k_ipm_group<M, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ipm_group<M, G, MINB>, GRP_WARPS * 32, smem));
-        if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_group does not fit on an SM");
-        if (const char* e = getenv("NMPC_GRP_BPS")) { int v = atoi(e); if (v >= 1 && v < nb) nb = v; }
-        blocks_per_sm = nb;
-    }
-    int nsm = 0;
-    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
-    const int per_block = GRP_WARPS * GP::NSLOT;
-    int blocks = nsm * blocks_per_sm;
-    const int need = (n + per_block - 1) / per_block;
-    if (blocks > need) blocks = need;
-    s->grp_blocks = blocks;
-    CK(cudaMemsetAsync(s->d_cnt, 0, sizeof(int), st));
-    k_ipm_group<M, G, MINB><<<blocks, GRP_WARPS * 32, smem, st>>>(i0, n, tb, d_We, ldWe, o, s->d_ws, s->d_cnt, out);
-    CK(cudaGetLastError());
-    return 0;
-}
 
 template <class M>
 static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
@@ -802,20 +922,12 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
         cudaEvent_t* ev = &s->ev[(size_t)c * 4];
         CK(cudaEventRecord(ev[0], st));
         dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1), g0((n + LING_BLOCK - 1) / LING_BLOCK, NSTAGE + 1);
-        k_linearize_g<M><<<g0, LING_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, o, s->d_ws);
+        k_linearize_g<M><<<g0, LING_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, o, s->d_ws_g);
         CK(cudaEventRecord(ev[1], st));
-        const int G = s->grp_G;
-        if constexpr (S::NV == 2) {
-            if (G == 8) rc = launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, B, o, out, st);
-            else if (G == 16) rc = launch_group<M, 16, 3>(s, i0, n, tb, d_We, B, o, out, st);
-            else rc = launch_group<M, 32, 3>(s, i0, n, tb, d_We, B, o, out, st);
-        } else {
-            if (G == 32) rc = launch_group<M, 32, 2>(s, i0, n, tb, d_We, B, o, out, st);
-            else rc = launch_group<M, 16, 2>(s, i0, n, tb, d_We, B, o, out, st);
-        }
+        rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nullptr, nullptr, nullptr}, st);
         if (rc) return rc;
         CK(cudaEventRecord(ev[2], st));
-        k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
+        k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws_g, s->d_qp_status, d_status);
         CK(cudaEventRecord(ev[3], st));
         s->last_launches += 3;
     }
@@ -840,7 +952,7 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
     if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
     if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
     CK(cudaEventRecord(s->ev_total[0], st));
-    if (s->k3_group) {
+    if (s->k3_group == 1) {
         switch (s->model) {
             case 0: rc = solve_device_group<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
             case 1: rc = solve_device_group<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;

@@ -109,7 +109,7 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
         std::vector<typename GP::Lane> lanes(32);
         std::vector<double> sm(GP::WARP_D, 0.0);
         for (int l = 0; l < 32; l++) GP::init_lane(lanes[l], l, 0);
-        GP::run_warp(lanes.data(), sm.data(), ws.data(), 0, B, &next, tb, We_inst ? WeT.data() : nullptr, B, *o, out);
+        GP::run_warp(lanes.data(), sm.data(), ws.data(), 0, B, &next, tb, We_inst ? WeT.data() : nullptr, B, *o, out, GrpResume{nullptr, nullptr, nullptr});
     }
     for (int i = 0; i < B; i++) {
         status[i] = qs[i]; iters[i] = qi[i];
@@ -138,5 +138,104 @@ extern "C" int emul_rti_group(int model, int G, int B, const double* W, const do
     if (model == 2 && G == 16) RG(TricModel, 16);
     if (model == 2 && G == 32) RG(TricModel, 32);
 #undef RG
+    return -1;
+}
+
+// ---- hybrid schedule: K iterations of the per-lane sweeps, then the unfinished instances are handed to the
+// lane-group kernel in the middle of an iteration (what solve_device_hybrid does on the device) ----
+template <class M, int G>
+static int run_hybrid(int K, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                      const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                      const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                      double* x, double* u, int* status, int* iters, double* stats)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    using GP = Grp<M, G>;
+    using GR = typename GP::R;
+    constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
+    std::vector<double> lti(NSTAGE * 4 * NV);
+    for (int k = 0; k < NSTAGE; k++) {
+        double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
+        S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+    }
+    std::vector<double> stg((NSTAGE + 1) * GP::TROW, 0.0);
+    for (int k = 0; k < NSTAGE; k++) {
+        for (int i = 0; i < 4 * NV; i++) stg[k * GP::TROW + i] = lti[k * 4 * NV + i];
+        stg[k * GP::TROW + GP::LT_ONE] = 1.0;
+        for (int i = 0; i < S::NY; i++) stg[k * GP::TROW + GP::T_W + i] = W[k * S::NY + i];
+    }
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, stg.data()};
+    std::vector<std::vector<double>> tiles(B, std::vector<double>(R::tile_doubles, 0.0));
+    std::vector<typename S::LaneCtl> ctl(B);
+    std::vector<int> qs(B, -1), qi(B, 0), list;
+    std::vector<double> st((size_t)8 * B, 0.0);
+    std::vector<double> WeT;
+    if (We_inst) { WeT.resize((size_t)NX * B); for (int i = 0; i < B; i++) for (int j = 0; j < NX; j++) WeT[(size_t)j * B + i] = We_inst[(size_t)i * NX + j]; }
+    std::vector<typename S::LaneCtl> ctl_g;
+    for (int i = 0; i < B; i++) {
+        double* base = tiles[i].data() + (i % LANES);
+        double* xi = x + (size_t)i * (NSTAGE + 1) * NX;
+        double* ui = u + (size_t)i * NSTAGE * NU;
+        const double* yi = yref + (size_t)i * (NSTAGE + 1) * nyref;
+        const double* wei = We_inst ? We_inst + (size_t)i * NX : We;
+        for (int k = 0; k <= NSTAGE; k++)
+            S::linearize_stage(k, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU, xi + (k < NSTAGE ? k + 1 : k) * NX,
+                               yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei,
+                               base + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES, base + R::OFF_IT + (size_t)k * R::NF_IT * LANES);
+        typename S::LaneCtl& c = ctl[i];
+        c.init(true);
+        double scratch[S::CarryB::SC_N * S::PSTRIDE];
+        S::template run_phase<S::SW_B_FIRST>(base, tb, wei, *o, false, c, scratch);
+        for (int it = 0; it < K && !c.done; it++) {
+            S::template run_phase<S::SW_FDF>(base, tb, wei, *o, false, c, scratch);
+            S::template run_phase<S::SW_B>(base, tb, wei, *o, false, c, scratch);
+        }
+        if (c.done) {
+            qs[i] = c.status; qi[i] = c.iter;
+            for (int q = 0; q < 4; q++) st[(size_t)q * B + i] = c.nrm[q];
+            st[(size_t)4 * B + i] = c.mu; st[(size_t)5 * B + i] = c.lin_res; st[(size_t)6 * B + i] = c.nfb;
+        } else { list.push_back(i); ctl_g.push_back(c); }
+    }
+    const int nres = (int)list.size();
+    std::vector<double> ws((size_t)std::max(nres, 1) * GR::inst_doubles, 0.0);
+    for (int q = 0; q < nres; q++)
+        for (int k = 0; k <= NSTAGE; k++)
+            GP::tile_to_record(tiles[list[q]].data() + (list[q] % LANES), k, GP::rec_of(ws.data(), q, k));
+    GrpOut out{qs.data(), qi.data(), st.data(), B};
+    int next = 0;
+    {
+        std::vector<typename GP::Lane> lanes(32);
+        std::vector<double> sm(GP::WARP_D, 0.0);
+        for (int l = 0; l < 32; l++) GP::init_lane(lanes[l], l, 0);
+        GP::run_warp(lanes.data(), sm.data(), ws.data(), 0, 0, &next, tb, We_inst ? WeT.data() : nullptr, B, *o, out,
+                     GrpResume{&nres, list.data(), ctl_g.data()});
+    }
+    std::vector<int> map(B, -1);
+    for (int q = 0; q < nres; q++) map[list[q]] = q;
+    for (int i = 0; i < B; i++) {
+        status[i] = qs[i]; iters[i] = qi[i];
+        if (stats) for (int q = 0; q < 7; q++) stats[i * 8 + q] = st[(size_t)q * B + i];
+        double* xi = x + (size_t)i * (NSTAGE + 1) * NX;
+        double* ui = u + (size_t)i * NSTAGE * NU;
+        if (qs[i] == 0 || qs[i] == 1)
+            for (int k = 0; k <= NSTAGE; k++) {
+                if (map[i] >= 0) S::template step_stage<GR, 1>(k, GP::rec_of(ws.data(), map[i], k), x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
+                else S::step_stage(k, tiles[i].data() + (i % LANES) + R::OFF_IT + (size_t)k * R::NF_IT * LANES, x0bar + (size_t)i * NX, xi + k * NX, ui + (k < NSTAGE ? k : 0) * NU);
+            }
+    }
+    return nres;
+}
+
+extern "C" int emul_rti_hybrid(int model, int K, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                               const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                               const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                               double* x, double* u, int* status, int* iters, double* stats)
+{
+#define RH(MODEL, GG) return run_hybrid<MODEL, GG>(K, B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats)
+    if (model == 0) RH(DiffModel, 8);
+    if (model == 1) RH(Omni4Model, 16);
+    if (model == 2) RH(TricModel, 8);
+#undef RH
     return -1;
 }

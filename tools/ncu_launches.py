@@ -28,10 +28,11 @@ def main(path, json_out=None, model=None, batch=None):
     names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd', '5': 'FDF'}
     for (i, k), m in data.items():
         kind = re.search(r'k_sweep<([\w:]+), (?:\(int\))?(\d)>', k)
-        name = names[kind.group(2)] if kind else k[:24]
+        grp = 'k_ipm_group' in k
+        name = names[kind.group(2)] if kind else ('K3group' if grp else k[:24])
         t = num(m, 'gpu__time_duration.sum'); rd = num(m, 'dram__bytes_read.sum'); wr = num(m, 'dram__bytes_write.sum')
         tot += t
-        if kind:
+        if kind or grp:
             k3_bytes += rd + wr; k3_ms += t
         extra = ''
         for key, lab in (('smsp__inst_executed.sum', 'inst'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'),
