@@ -1036,8 +1036,15 @@ struct Rti {
             run_phase<SW_BD>(tile_lane, tb, We, o, false, c, scratch);
             run_phase<SW_FD>(tile_lane, tb, We, o, false, c, scratch);
             if (!c.done && c.fb) {
-                run_phase<SW_BD>(tile_lane, tb, We, o, true, c, scratch);
-                run_phase<SW_FD>(tile_lane, tb, We, o, true, c, scratch);
+                if (fallback) {
+                    // hybrid schedule: the rare lane whose corrector overshoots would make its whole warp (and with it
+                    // the launch) wait for two more sweeps; it leaves the lockstep path here (done = 2) and the lane-group
+                    // kernel redoes this iteration's solve phase, centering repeat included, from the factorisation
+                    c.done = 2;
+                } else {
+                    run_phase<SW_BD>(tile_lane, tb, We, o, true, c, scratch);
+                    run_phase<SW_FD>(tile_lane, tb, We, o, true, c, scratch);
+                }
             }
         } else {
             if (c.done) return;

@@ -141,7 +141,8 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
 template <class M, int KIND>
 __global__ void __launch_bounds__(LANES * SW_TILES, KIND == 5 ? 8 : 4)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
-        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min)
+        double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min,
+        int defer_fb)
 {
     using S = Rti<M>;
     using R = typename S::R;
@@ -164,7 +165,7 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
             for (int j = 0; j < S::NX; j++) We[j] = We_inst ? We_inst[(size_t)j * B + i0 + li] : tb.We[j];
         }
         double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
-        S::template run_phase<KIND>(tile_lane, tb, We, o, false, c, scratch + threadIdx.x);
+        S::template run_phase<KIND>(tile_lane, tb, We, o, KIND == S::SW_FDF && defer_fb != 0, c, scratch + threadIdx.x);
     }
     if (active && (run || KIND == S::SW_B_FIRST)) ctl_store<S>(c, ctl_d, ctl_i, ldc, li);
     if (KIND == S::SW_B_FIRST || KIND == S::SW_B) {
@@ -288,11 +289,12 @@ __global__ void k_handover_compact(int nchunk, int ldc, const double* __restrict
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= nchunk) return;
     int q = -1;
-    if (ctl_i[li] == 0) {                              // row 0 = done
+    if (ctl_i[li] != 1) {                              // row 0 = done: 0 iterating, 2 left the lockstep path at a centering repeat
         q = atomicAdd(nres, 1);
         list[q] = li;
         typename S::LaneCtl c;
         ctl_load<S>(c, ctl_d, ctl_i, ldc, li);
+        c.done = 0;
         reinterpret_cast<typename S::LaneCtl*>(ctl_out)[q] = c;
     }
     map[li] = q;
@@ -853,7 +855,7 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 attr_set = true;
             }
             CK(cudaMemsetAsync(s->d_cnt, 0, (size_t)s->cnt_cap * sizeof(int), st));
-            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 1);
+            k_sweep<M, S::SW_B_FIRST><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act, act, 1, 0);
             s->last_launches++;
             // hybrid schedule: the lockstep sweeps run while at least gate_min instances iterate (a sweep costs the
             // same whether 100% or 10% of the lanes are active), at most kmax iterations; whatever is unfinished is
@@ -863,8 +865,8 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
             int gate_min = 1;
             if (hybrid) { gate_min = (int)(s->hyb_frac * n); if (gate_min < 1) gate_min = 1; }
             for (int it = 0; it < kmax; it++) {
-                k_sweep<M, S::SW_FDF><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, gate_min);
-                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, gate_min);
+                k_sweep<M, S::SW_FDF><<<nb, nt, 0, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, nullptr, gate_min, hybrid ? 1 : 0);
+                k_sweep<M, S::SW_B><<<nb, nt, smB, st>>>(B, i0, n, ldc, tb, d_We, o, s->d_ws, s->d_ctl_d, s->d_ctl_i, act + it, act + it + 1, gate_min, 0);
                 s->last_launches += 2;
             }
             k_ipm_finish<<<(n + 255) / 256, 256, 0, st>>>(B, i0, n, ldc, s->d_ctl_d, s->d_ctl_i, s->d_qp_status, d_qp_iter, d_stats);

@@ -188,9 +188,10 @@ static int run_hybrid(int K, int B, const double* W, const double* We, const dou
         double scratch[S::CarryB::SC_N * S::PSTRIDE];
         S::template run_phase<S::SW_B_FIRST>(base, tb, wei, *o, false, c, scratch);
         for (int it = 0; it < K && !c.done; it++) {
-            S::template run_phase<S::SW_FDF>(base, tb, wei, *o, false, c, scratch);
+            S::template run_phase<S::SW_FDF>(base, tb, wei, *o, true, c, scratch);      // true: defer a centering repeat (done = 2)
             S::template run_phase<S::SW_B>(base, tb, wei, *o, false, c, scratch);
         }
+        if (c.done == 2) c.done = 0;
         if (c.done) {
             qs[i] = c.status; qi[i] = c.iter;
             for (int q = 0; q < 4; q++) st[(size_t)q * B + i] = c.nrm[q];
