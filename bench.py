@@ -2,7 +2,8 @@
 """Benchmark of the SQP-RTI hot path (BASELINE.json metric: batched OCP solves/sec, fp64).
 
 A "step" = one SQP-RTI iteration of every instance of the batch from the reset (all-zero)
-iterate: K1+K2 linearise, K3 interior-point QP, K4 step.  Workload at N=1: BASELINE config 2
+iterate: K1+K2 linearise, K3 interior-point QP (hybrid schedule: lockstep horizon sweeps while most
+instances iterate, then the persistent lane-group kernel for the rest), K4 step.  Workload at N=1: BASELINE config 2
 (diff model, 65,536 random initial states / reference paths, SURVEY.md Appendix D inputs).
 With N>1 every rank solves its own 65,536-instance shard (weak scaling, no collective on the
 solve path; torch.distributed is only used for the barrier and the max-over-ranks time).
@@ -292,20 +293,22 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": MODEL, "batch_per_gpu": B, "N": spec.n, "iterate": "reset (zero) before every step",
-                   "l2": "inputs (131 MB) + K3 workspace streamed every sweep (5.6 GB) exceed the 126 MB L2; no explicit flush",
+                   "l2": "inputs (131 MB) and the K3 workspace (5.6 GB tile state streamed by every sweep, 3 GB of group records) "
+                         "exceed the 126 MB L2 many times over; no explicit flush",
+                   "k3_schedule": os.environ.get("NMPC_K3", "hybrid"),
                    "mean_qp_iter": mean_iter, "status_nonzero": status_bad},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "api": "nmpc_rti_solve_host (C ABI, pinned host buffers)"},
         "gpu_launches": launches,
         "kernel_ms": kt,
-        "roofline": {"kernel": "K3 interior point = all k_sweep<B_FIRST|FDF|B> launches of one step", "bound": "hbm",
+        "roofline": {"kernel": "K3 interior point = the k_sweep<B_FIRST|FDF|B>, k_handover_* and k_ipm_group launches of one step", "bound": "hbm",
                      "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": alg_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                      "note": "achieved = algorithmic bytes (17,512 B/solve, SURVEY 8d) x instances / K3 time per step "
                              "(CUDA events inside the library, on the launching stream); traffic = measured DRAM bytes of "
-                             "the same launches (ncu): K3 streams the 85 KB interior-point state of every instance "
-                             "through HBM each sweep, see roofline_stream and DESIGN.md 5"},
+                             "the same launches (ncu launch list under profiles/): K3 streams the 85 KB interior-point state "
+                             "of every instance through HBM each sweep, see roofline_stream and DESIGN.md 5"},
         "roofline_stream": None if traffic is None else {
             "kernel": "K3", "bound": "hbm", "achieved": traffic / qp_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": traffic / qp_s / 1e9 / hbm_peak,

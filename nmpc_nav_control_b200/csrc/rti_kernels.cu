@@ -499,6 +499,7 @@ struct nmpc_solver {
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
     int hyb_kmax = 12; double hyb_frac = 0.5;
+    int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
     size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
@@ -605,6 +606,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     s->tile_doubles = tile_doubles_of(model);
     if (const char* e = getenv("NMPC_K3")) s->k3_group = !strcmp(e, "sweep") ? 0 : !strcmp(e, "group") ? 1 : 2;
     if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
+    if (const char* e = getenv("NMPC_HYB_MIN")) { int v = atoi(e); if (v >= 0) s->hyb_min = v; }
     if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
     s->grp_G = (model == 1) ? 16 : 8;
     if (const char* e = getenv("NMPC_GRP_G")) { int v = atoi(e); if ((v == 8 && model != 1) || v == 16 || v == 32) s->grp_G = v; }
@@ -954,7 +956,7 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
     if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
     if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
     CK(cudaEventRecord(s->ev_total[0], st));
-    if (s->k3_group == 1) {
+    if (s->k3_group == 1 || (s->k3_group == 2 && B < s->hyb_min)) {
         switch (s->model) {
             case 0: rc = solve_device_group<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
             case 1: rc = solve_device_group<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;

@@ -117,8 +117,10 @@ def test_full_size_properties():
     torch.cuda.synchronize()
     x2, u2 = s2.get_iterate(4096)
     xa, ua = s.get_iterate(1000 + 4096)
-    assert np.array_equal(x2, xa[1000:]) and np.array_equal(u2, ua[1000:])
+    # (the large batch runs the hybrid K3 schedule, the small one the lane-group kernel alone: same iteration path,
+    # different summation order, so equal iteration counts and agreement inside the parity tolerance, not bit for bit)
     assert torch.equal(out2["qp_iter"], out["qp_iter"][1000:1000 + 4096])
+    assert parity_report(x2, xa[1000:])[0] == 0 and parity_report(u2, ua[1000:])[0] == 0
 
 
 @pytest.mark.parametrize("name", ["diff", "omni4", "tric"])

@@ -25,15 +25,21 @@ def main(path, json_out=None, model=None, batch=None):
         data.setdefault(key, {})[d['Metric Name']] = (d['Metric Value'], d['Metric Unit'])
     tot = 0.0
     k3_bytes = 0.0; k3_ms = 0.0
+    step = -1; step_bytes = {}; step_ms = {}; step_n = {}      # per solver step (a step starts at its linearise kernel)
     names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd', '5': 'FDF'}
     for (i, k), m in data.items():
         kind = re.search(r'k_sweep<([\w:]+), (?:\(int\))?(\d)>', k)
-        grp = 'k_ipm_group' in k
-        name = names[kind.group(2)] if kind else ('K3group' if grp else k[:24])
+        grp = 'k_ipm_group' in k or 'k_handover' in k or 'k_ipm_finish' in k
+        name = names[kind.group(2)] if kind else ('K3group' if 'k_ipm_group' in k else k[:24])
+        if 'k_linearize' in k:
+            step += 1
         t = num(m, 'gpu__time_duration.sum'); rd = num(m, 'dram__bytes_read.sum'); wr = num(m, 'dram__bytes_write.sum')
         tot += t
         if kind or grp:
             k3_bytes += rd + wr; k3_ms += t
+            if step >= 0:
+                step_bytes[step] = step_bytes.get(step, 0.0) + rd + wr; step_ms[step] = step_ms.get(step, 0.0) + t
+                step_n[step] = step_n.get(step, 0) + 1
         extra = ''
         for key, lab in (('smsp__inst_executed.sum', 'inst'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'),
                          ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
@@ -43,10 +49,13 @@ def main(path, json_out=None, model=None, batch=None):
                 extra += f' {lab}={num(m, key):.4g}'
         print(f'{i:3d} {name:8s} t={t:.3f}ms rd={rd / 1e9:.2f}GB wr={wr / 1e9:.2f}GB bw={(rd + wr) / max(t, 1e-9) / 1e9:.2f}TB/s{extra}')
     print(f'total {tot:.3f} ms over {len(data)} launches; K3 launches: {k3_ms:.3f} ms, {k3_bytes / 1e9:.2f} GB DRAM')
+    if step_bytes:
+        print('per step (K3 launches only): ' + ', '.join(f'step {q}: {step_n[q]} launches {step_ms[q]:.3f} ms {step_bytes[q] / 1e9:.2f} GB' for q in sorted(step_bytes)))
     if json_out:
         import json
-        json.dump({"model": model, "batch": batch, "dram_bytes_per_step": k3_bytes, "k3_ms_under_ncu": k3_ms,
-                   "launches": len(data), "source": path}, open(json_out, "w"))
+        q = 0      # the first step of the capture is complete (the last one may be cut by ncu -c)
+        json.dump({"model": model, "batch": batch, "dram_bytes_per_step": step_bytes[q], "k3_ms_under_ncu": step_ms[q],
+                   "k3_launches_per_step": step_n[q], "source": path}, open(json_out, "w"), indent=1)
 
 
 if __name__ == '__main__':
