@@ -25,6 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
 
 METRIC = "batched OCP solves/sec (fp64 SQP-RTI)"
 UNIT = "solves/s"
