@@ -34,6 +34,9 @@
 #define GRP_NL 32
 #define GRP_SYNC() ((void)0)
 #endif
+#ifndef NMPC_GRP_DEPTH
+#define NMPC_GRP_DEPTH 2
+#endif
 #define GRP_PHASE_BEGIN(lanes) { for (int ln_ = 0; ln_ < GRP_NL; ++ln_) { Lane& L = (lanes)[ln_];
 #define GRP_PHASE_END } GRP_SYNC(); }
 
@@ -93,10 +96,11 @@ NMPC_HD void grp_cp_commit()
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 #endif
 }
-NMPC_HD void grp_cp_wait_all()
+template <int PENDING>
+NMPC_HD void grp_cp_wait()
 {
 #if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    asm volatile("cp.async.wait_group %0;\n" :: "n"(PENDING) : "memory");
 #endif
 }
 NMPC_HD int grp_fetch_add(int* ctr)
@@ -188,9 +192,34 @@ struct Grp {
     static_assert(G >= NX && G >= NCT && G > NC && 32 % G == 0, "one state column, one constraint, one component per lane");
     using R = GRec<NV>;
 
+    enum { SW_B = 0, SW_F = 1, SW_BD = 2, SW_FD = 3 };
+    NMPC_HD static constexpr int imax(int a, int b) { return a > b ? a : b; }
+    // the two record ranges [A0, A1), [B0, B1) a sweep reads (GRec), its compact image [A | B] and prefetch depth
+    template <int KIND> struct Img {
+        static constexpr int A0 = KIND == SW_B ? R::Q : KIND == SW_BD ? R::E : R::DLB;
+        static constexpr int A1 = KIND == SW_B ? R::LHD : KIND == SW_F ? R::DZA : R::LH;
+        static constexpr int B0 = KIND == SW_B ? R::MC : KIND == SW_F ? R::T : KIND == SW_BD ? R::MC : R::DZA;
+        static constexpr int B1 = KIND == SW_B ? R::NREC : KIND == SW_BD ? R::LAM : R::PI;
+        static constexpr int SIZE = (A1 - A0) + (B1 - B0);
+        static constexpr int D = NMPC_GRP_DEPTH;         // measured: 3-4 stages in flight change nothing (a lone warp is bound by its
+                                                         // ~2,500 dependent instructions per stage set, not by DRAM latency), 2 costs the least shared memory
+        // virtual record bases: a(img)[R::X] for a field X of range A, b(img)[R::X] for a field of range B
+        NMPC_HD static double* a(double* img) { return img - A0; }
+        NMPC_HD static double* b(double* img) { return img + (A1 - A0) - B0; }
+        NMPC_HD static const double* a(const double* img) { return img - A0; }
+        NMPC_HD static const double* b(const double* img) { return img + (A1 - A0) - B0; }
+    };
+
     // ---- shared-memory scratch of one slot (doubles) ----------------------------------------
-    static constexpr int O_IN = 0;                        // [2][NREC] double-buffered record image
-    static constexpr int O_CAR = O_IN + 2 * R::NREC;      // [2][3][NX] carries of the B sweep: pio, dpi, xn
+    // ring of compact stage images: a sweep of kind K keeps Img<K>::D stages in flight, each image holding only the
+    // two record ranges the sweep reads (Img<K>::SIZE doubles).  Depth matters for a warp that runs alone (the
+    // stragglers of a batch, batch 1): its stage takes 0.3-1 us of compute against > 1 us of DRAM latency.
+    static constexpr int O_IN = 0;
+    static constexpr int RING = imax(imax(imax(Img<SW_B>::D * Img<SW_B>::SIZE, Img<SW_F>::D * Img<SW_F>::SIZE),
+                                          imax(Img<SW_BD>::D * Img<SW_BD>::SIZE, Img<SW_FD>::D * Img<SW_FD>::SIZE)),
+                                     G * 8 /* the end-of-sweep reductions borrow the ring */);
+    static constexpr int DMAX = imax(imax(Img<SW_B>::D, Img<SW_F>::D), imax(Img<SW_BD>::D, Img<SW_FD>::D));
+    static constexpr int O_CAR = O_IN + RING;             // [2][3][NX] carries of the B sweep: pio, dpi, xn
                                                           //   (F: dx [2][NX]; Bd: dp [2][NX])
     static constexpr int O_PV = O_CAR + 6 * NX;           // NX   gradient of the cost-to-go
     static constexpr int O_RB = O_PV + NX;                // NX   dynamics residual
@@ -208,15 +237,15 @@ struct Grp {
     static constexpr int CTL_D = (int)((sizeof(LaneCtl) + 7) / 8);
     static constexpr int O_RED = O_IN;                    // [G][8] reductions at the end of a sweep / queue hand-out (the record image is dead there)
     static constexpr int O_END = O_CTL + CTL_D;
-    static_assert(G * 8 <= 2 * R::NREC, "reduction buffer must fit into the record image");
+    static_assert(G * 8 <= RING, "reduction buffer must fit into the image ring");
     // slot stride: even (16-byte copies) and = 8 mod 16 so that equal offsets of neighbouring slots
     // fall into different bank groups
     static constexpr int SLOT_D = ((O_END + 15) / 16) * 16 + 8;
     // per-warp image of the stage table row (double buffered like the records): [lte (4NV+2) | W (NY)], rows padded
     static constexpr int T_W = (LTE + 1) & ~1;            // offset of the weights in a row
     static constexpr int TROW = T_W + ((NY + 1) & ~1);
-    static constexpr int O_TAB = SLOT_D * NSLOT;
-    static constexpr int WARP_D = SLOT_D * NSLOT + 2 * TROW;   // doubles of shared memory per warp
+    static constexpr int O_TAB = SLOT_D * NSLOT;          // [DMAX][TROW] ring of stage-table rows
+    static constexpr int WARP_D = SLOT_D * NSLOT + DMAX * TROW;   // doubles of shared memory per warp
     static_assert(TROW / 2 <= 32, "one 16-byte chunk of the stage table per lane");
 
     // static-index products with J = [A B] (registers only): (column w of J) . v, w in [x; u] order
@@ -352,49 +381,45 @@ struct Grp {
             if (c + 2 * r < d1) grp_cp16(dst + c + 2 * r, src + c + 2 * r);
     }
 
-    enum { SW_B = 0, SW_F = 1, SW_BD = 2, SW_FD = 3 };
 
     // the stage-table row of stage k into image `buf` of the warp (every lane of the warp, running slot or not)
-    NMPC_HD static void issue_tab(const Lane& L, double* sm, const double* src, int buf)
+    NMPC_HD static void issue_tab(const Lane& L, double* sm, const double* src, int slot)
     {
-        if (2 * L.wl < TROW) grp_cp16(sm + L.to + buf * TROW + 2 * L.wl, src);
+        if (2 * L.wl < TROW) grp_cp16(sm + L.to + slot * TROW + 2 * L.wl, src);
     }
-    // start of a sweep: record / stage-table pointers one stage before the first one (k0), prefetch of k0
+    // the two ranges of one record into an image
+    template <int KIND>
+    NMPC_HD static void issue(const Lane& L, const double* src, double* img)
+    {
+        copy_range(Img<KIND>::a(img), src, Img<KIND>::A0, Img<KIND>::A1, L.r);
+        copy_range(Img<KIND>::b(img), src, Img<KIND>::B0, Img<KIND>::B1, L.r);
+    }
+    // prefetch of the stage `ahead` stages after the current one (pointers L.grec / L.tsrc) into ring slot `slot`;
+    // one cp.async group per stage, committed by every lane whether it copied or not
+    template <int KIND, int DIR>
+    NMPC_HD static void prefetch(const Lane& L, double* sm, int ahead, int slot, bool valid)
+    {
+        if (valid) {
+            issue_tab(L, sm, L.tsrc + DIR * ahead * TROW, slot);
+            if (L.run) issue<KIND>(L, L.grec + DIR * ahead * R::NREC, sm + L.so + O_IN + slot * Img<KIND>::SIZE);
+        }
+        grp_cp_commit();
+    }
+    // start of a sweep at stage k0: record / stage-table pointers one stage before it, first D-1 stages in flight
     template <int KIND, int DIR>
     NMPC_HD static void begin_sweep(Lane& L, double* sm, double* ws, const Tables& tb, int k0)
     {
         L.tsrc = grp_pin_ptr(tb.stg + (size_t)k0 * TROW + 2 * L.wl - DIR * TROW);
-        if (L.run) {
-            L.grec = grp_pin_ptr(rec_of(ws, L.li, k0) - DIR * R::NREC);
-            issue<KIND>(L, L.grec + DIR * R::NREC, sm + L.so + O_IN);
-        }
-        issue_tab(L, sm, L.tsrc + DIR * TROW, 0);
-        grp_cp_commit();
+        if (L.run) L.grec = grp_pin_ptr(rec_of(ws, L.li, k0) - DIR * R::NREC);
+#pragma unroll
+        for (int j = 0; j < Img<KIND>::D - 1; j++) prefetch<KIND, DIR>(L, sm, j + 1, j, true);
     }
-    // top of a stage: advance to it, wait for its image
-    template <int DIR>
+    // top of a stage: advance to it, wait for its image (D-2 younger groups may still be in flight)
+    template <int KIND, int DIR>
     NMPC_HD static void begin_stage(Lane& L)
     {
         L.grec += DIR * R::NREC; L.tsrc += DIR * TROW;
-        grp_cp_wait_all();
-    }
-
-    template <int KIND>
-    NMPC_HD static void issue(const Lane& L, const double* src, double* dst)
-    {
-        if (KIND == SW_B) {
-            copy_range(dst, src, R::Q, R::LHD, L.r);
-            copy_range(dst, src, R::MC, R::NREC, L.r);
-        } else if (KIND == SW_F) {
-            copy_range(dst, src, R::DLB, R::DZA, L.r);
-            copy_range(dst, src, R::T, R::PI, L.r);
-        } else if (KIND == SW_BD) {
-            copy_range(dst, src, R::E, R::LH, L.r);
-            copy_range(dst, src, R::MC, R::LAM, L.r);
-        } else {
-            copy_range(dst, src, R::DLB, R::LH, L.r);
-            copy_range(dst, src, R::DZA, R::PI, L.r);
-        }
+        grp_cp_wait<Img<KIND>::D - 2>();
     }
 
     // all-gather of up to 8 per-lane partials through the slot scratch: after the call every lane
@@ -460,21 +485,21 @@ struct Grp {
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
-            const int k = NSTAGE - s, buf = s & 1;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
+            constexpr int D = Img<SW_B>::D;
+            const int k = NSTAGE - s, slot = s % D, pslot = (s + D - 1) % D;
+            const bool hasU = k < NSTAGE, hasX = k > 0, pvalid = s + D - 1 <= NSTAGE;
             GRP_PHASE_BEGIN(lanes)
-                begin_stage<-1>(L);
+                begin_stage<SW_B, -1>(L);
             GRP_PHASE_END
             // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
             GRP_PHASE_BEGIN(lanes)
-                if (s < NSTAGE) issue_tab(L, sm, L.tsrc - TROW, buf ^ 1);
-                if (!L.run) { grp_cp_commit(); continue; }
-                const double* ltk = sm + L.to + buf * TROW;
+                prefetch<SW_B, -1>(L, sm, D - 1, pslot, pvalid);
+                if (!L.run) continue;
+                const double* ltk = sm + L.to + slot * TROW;
                 double* scr = sm + L.so;
                 double* grec = L.grec;
-                if (s < NSTAGE) issue<SW_B>(L, grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
-                grp_cp_commit();
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<SW_B>::SIZE;
+                const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
                 const double a_step = L.astep;
                 if (L.r < NCT) {
                     const int c = L.r;
@@ -482,8 +507,8 @@ struct Grp {
                     double rpart = 0.0, lpart = 0.0, gpart = 0.0, Gp = 0.0;
                     if (actc) {
                         const double sg = L.ct_s;
-                        const double dbd = rec[R::DLB + c], z = rec[R::Z + L.ct_z], dz = rec[R::DZ + L.ct_z];
-                        const double lam = rec[R::LAM + c], t = rec[R::T + c], mc = rec[R::MC + c];
+                        const double dbd = rec[R::DLB + c], z = rec2[R::Z + L.ct_z], dz = rec2[R::DZ + L.ct_z];
+                        const double lam = rec2[R::LAM + c], t = rec2[R::T + c], mc = rec2[R::MC + c];
                         const double rd = sg * (dbd - z) + t;
                         const double rm = lam * t - o.tau_min + L.mcw * mc - L.sigmu;
                         const double dt = sg * dz - rd;
@@ -523,10 +548,11 @@ struct Grp {
                 if (!L.run) continue;
                 double* scr = sm + L.so;
                 double* grec = L.grec;
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<SW_B>::SIZE;
+                const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
                 const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
                 double* carn = scr + O_CAR + ((s & 1) ^ 1) * 3 * NX;
-                const double* ltk = sm + L.to + buf * TROW;
+                const double* ltk = sm + L.to + slot * TROW;
                 const double a_step = L.astep;
                 if (L.r < NC) {
                     // generic component: column q = r of the pose rows E
@@ -539,9 +565,9 @@ struct Grp {
                     const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
                     const double v3 = jt_comp(L, e0, e1, e2, k1, k2, scr + O_PV);
                     const double H = hasU ? tb.dt * ltk[T_W + L.cq_y] : L.We_c;
-                    const double qv = rec[R::Q + L.cq_z], z = rec[R::Z + L.cq_z], dz = rec[R::DZ + L.cq_z];
+                    const double qv = rec[R::Q + L.cq_z], z = rec2[R::Z + L.cq_z], dz = rec2[R::DZ + L.cq_z];
                     const bool haspi = isx && hasX;
-                    const double pin = haspi ? rec[R::PI + (isx ? L.cq_x : 0)] : 0.0;
+                    const double pin = haspi ? rec2[R::PI + (isx ? L.cq_x : 0)] : 0.0;
                     const double* cl = scr + O_CB + 4 * L.cq_bl;
                     const double* cu = scr + O_CB + 4 * L.cq_bu;
                     double r = qv + H * z - pin + v1 + H * dz + v2;
@@ -570,8 +596,8 @@ struct Grp {
                     const int j = L.r == XL ? 0 : 1;
                     const double v1 = car[j], v2 = car[NX + j], v3 = scr[O_PV + j];      // all zero at the terminal stage
                     const double H = hasU ? tb.dt * ltk[T_W + j] : L.We_xy;
-                    const double qv = rec[R::Q + NU + j], z = rec[R::Z + NU + j], dz = rec[R::DZ + NU + j];
-                    const double pin = hasX ? rec[R::PI + j] : 0.0;
+                    const double qv = rec[R::Q + NU + j], z = rec2[R::Z + NU + j], dz = rec2[R::DZ + NU + j];
+                    const double pin = hasX ? rec2[R::PI + j] : 0.0;
                     const double r = qv + H * z - pin + v1 + H * dz + v2;
                     const double pin_n = hasX ? pin + a_step * r : 0.0;
                     const double zn = z + a_step * dz;
@@ -585,8 +611,8 @@ struct Grp {
                 }
                 if (hasU && L.r < NX) {
                     // dynamics residual, row r, at the new iterate (recomputed from the record: no exchange)
-                    const double rb = jrow(L.r, [&](int c) { return rec[R::Z + c] + a_step * rec[R::DZ + c]; },
-                                           [&](int j) { return rec[R::Z + NU + j] + a_step * rec[R::DZ + NU + j]; }, rec + R::E, ltk)
+                    const double rb = jrow(L.r, [&](int c) { return rec2[R::Z + c] + a_step * rec2[R::DZ + c]; },
+                                           [&](int j) { return rec2[R::Z + NU + j] + a_step * rec2[R::DZ + NU + j]; }, rec + R::E, ltk)
                                       + rec[R::B0 + L.r] - car[2 * NX + L.r];
                     L.nb = grp_maxabs(L.nb, rb);
                     scr[O_RB + L.r] = rb;
@@ -731,20 +757,20 @@ struct Grp {
         GRP_PHASE_END
 #pragma unroll 1
         for (int k = 0; k <= NSTAGE; k++) {
-            const int buf = k & 1;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
+            constexpr int D = Img<KIND>::D;
+            const int slot = k % D, pslot = (k + D - 1) % D;
+            const bool hasU = k < NSTAGE, hasX = k > 0, pvalid = k + D - 1 <= NSTAGE;
             GRP_PHASE_BEGIN(lanes)
-                begin_stage<1>(L);
+                begin_stage<KIND, 1>(L);
             GRP_PHASE_END
             // ---- F1: prefetch; s_a = lh_a + K_a . dx on the first NV lanes ------------------------------
             GRP_PHASE_BEGIN(lanes)
-                if (k < NSTAGE) issue_tab(L, sm, L.tsrc + TROW, buf ^ 1);
-                if (!L.run) { grp_cp_commit(); continue; }
+                prefetch<KIND, 1>(L, sm, D - 1, pslot, pvalid);
+                if (!L.run) continue;
                 double* scr = sm + L.so;
-                if (k < NSTAGE) issue<KIND>(L, L.grec + R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
-                grp_cp_commit();
                 if (!hasU || L.r >= NV) continue;
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<KIND>::SIZE;
+                const double* rec = Img<KIND>::a(img); const double* rec2 = Img<KIND>::b(img);
                 const double* dx = scr + O_CAR + (k & 1) * NX;
                 const int a = L.r;
                 double s0 = rec[(DELTA ? R::LHD : R::LH) + a], s1 = 0.0;
@@ -762,10 +788,11 @@ struct Grp {
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<KIND>::SIZE;
+                const double* rec = Img<KIND>::a(img); const double* rec2 = Img<KIND>::b(img);
                 double* grec = L.grec;
                 const double* dx = scr + O_CAR + (k & 1) * NX;
-                const double* ltk = sm + L.to + buf * TROW;
+                const double* ltk = sm + L.to + slot * TROW;
 #pragma unroll
                 for (int a = 0; a < NV; a++) L.du[a] = 0.0;
                 if (hasU) {
@@ -786,12 +813,12 @@ struct Grp {
                     const bool actc = (L.ct_u >= 0) ? hasU : hasX;
                     if (actc) {
                         double dzw = L.ct_x >= 0 ? dx[L.ct_x >= 0 ? L.ct_x : 0] : du_of(L.ct_u);
-                        if (DELTA) dzw += rec[R::DZA + L.ct_z];
+                        if (DELTA) dzw += rec2[R::DZA + L.ct_z];
                         const double sg = L.ct_s;
-                        const double lam = rec[R::LAM + c], t = rec[R::T + c], zb = rec[R::Z + L.ct_z];
+                        const double lam = rec2[R::LAM + c], t = rec2[R::T + c], zb = rec2[R::Z + L.ct_z];
                         const double rd = sg * (rec[R::DLB + c] - zb) + t;
                         double rm = lam * t - o.tau_min;
-                        if (DELTA) rm += mcw * rec[R::MC + c] - L.sigmu;
+                        if (DELTA) rm += mcw * rec2[R::MC + c] - L.sigmu;
                         const double dt = sg * dzw - rd;
                         const double dl = -(lam * dt + rm) / t;
                         if (!DELTA) grec[R::MC + c] = dt * dl;
@@ -807,12 +834,12 @@ struct Grp {
                 if (L.r < NX) {
                     double dzw = L.dxr;
                     if (!DELTA) grec[R::DZA + NU + L.r] = dzw;
-                    else grec[R::DZ + NU + L.r] = dzw + rec[R::DZA + NU + L.r];
+                    else grec[R::DZ + NU + L.r] = dzw + rec2[R::DZA + NU + L.r];
                 }
                 if (L.r < NV) {
                     double dzw = du_of(L.r);
                     if (!DELTA) grec[R::DZA + L.r] = dzw;
-                    else grec[R::DZ + L.r] = dzw + rec[R::DZA + L.r];
+                    else grec[R::DZ + L.r] = dzw + rec2[R::DZA + L.r];
                 }
                 if (hasU && L.r < NX) {
                     double xn = jrow(L.r, du_of, [&](int j) { return dx[j]; }, rec + R::E, ltk);
@@ -841,20 +868,20 @@ struct Grp {
         GRP_PHASE_END
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
-            const int k = NSTAGE - s, buf = s & 1;
-            const bool hasU = k < NSTAGE, hasX = k > 0;
+            constexpr int D = Img<SW_BD>::D;
+            const int k = NSTAGE - s, slot = s % D, pslot = (s + D - 1) % D;
+            const bool hasU = k < NSTAGE, hasX = k > 0, pvalid = s + D - 1 <= NSTAGE;
             GRP_PHASE_BEGIN(lanes)
-                begin_stage<-1>(L);
+                begin_stage<SW_BD, -1>(L);
             GRP_PHASE_END
             // ---- D1: q = J' dp + complementarity terms, one component per lane -----------------------
             GRP_PHASE_BEGIN(lanes)
-                if (s < NSTAGE) issue_tab(L, sm, L.tsrc - TROW, buf ^ 1);
-                if (!L.run) { grp_cp_commit(); continue; }
-                const double* ltk = sm + L.to + buf * TROW;
+                prefetch<SW_BD, -1>(L, sm, D - 1, pslot, pvalid);
+                if (!L.run) continue;
+                const double* ltk = sm + L.to + slot * TROW;
                 double* scr = sm + L.so;
-                if (s < NSTAGE) issue<SW_BD>(L, L.grec - R::NREC, scr + O_IN + (buf ^ 1) * R::NREC);
-                grp_cp_commit();
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<SW_BD>::SIZE;
+                const double* rec = Img<SW_BD>::a(img); const double* rec2 = Img<SW_BD>::b(img);
                 const double* dp = scr + O_CAR + (s & 1) * NX;
                 if (L.r < NC) {
                     const int q = L.r;
@@ -865,8 +892,8 @@ struct Grp {
                         qv = jt_comp(L, e0, e1, e2, ltk[L.cq_k1], ltk[L.cq_k2], dp);
                     }
                     if (L.cq_bl < NCT && (isx ? hasX : hasU)) {
-                        const double tl = rec[R::T + L.cq_bl], tu = rec[R::T + L.cq_bu];
-                        qv += (mcw * rec[R::MC + L.cq_bl] - L.sigmu) / tl - (mcw * rec[R::MC + L.cq_bu] - L.sigmu) / tu;
+                        const double tl = rec2[R::T + L.cq_bl], tu = rec2[R::T + L.cq_bu];
+                        qv += (mcw * rec2[R::MC + L.cq_bl] - L.sigmu) / tl - (mcw * rec2[R::MC + L.cq_bu] - L.sigmu) / tu;
                     }
                     if (isx) scr[O_GX + L.cq_x] = qv; else scr[O_GU + L.cq_z] = qv;
                 }
@@ -879,7 +906,8 @@ struct Grp {
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                const double* rec = scr + O_IN + buf * R::NREC;
+                const double* img = scr + O_IN + slot * Img<SW_BD>::SIZE;
+                const double* rec = Img<SW_BD>::a(img); const double* rec2 = Img<SW_BD>::b(img);
                 double* dpn = scr + O_CAR + ((s & 1) ^ 1) * NX;
                 if (hasU) {
 #pragma unroll
