@@ -121,7 +121,7 @@ def run_reference(args):
         return
     from oracle import orc
     cores = orc.max_threads()
-    sample = int(min(BATCH, max(1024, 64 * cores)))
+    sample = int(min(BATCH, max(16384, 512 * cores)))
     cpu_baseline(MODEL, min(sample, 1024))          # warm-up / page-in
     for _ in range(max(0, args.warmup - 1)):
         cpu_baseline(MODEL, sample)
@@ -282,11 +282,11 @@ def run_ours(args):
     if not args.no_cpu:
         from oracle import orc
         cores = orc.max_threads()
-        sample = int(min(BATCH, max(2048, 128 * cores)))
+        sample = BATCH                                  # the whole workload: ~10 s of CPU work for the three passes
         cpu_baseline(MODEL, 1024)
-        r = cpu_baseline(MODEL, sample, repeats=2)
+        r = cpu_baseline(MODEL, sample, repeats=3)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{sample} of the same diff instances, cold iterate, OpenMP one solve per core, best of 2 "
+               "sample": f"{sample} of the same diff instances, cold iterate, OpenMP one solve per core, best of 3 "
                          f"({r['seconds']:.2f} s); acados-algorithm restatement (oracle), not acados"}
 
     line = {
