@@ -59,11 +59,50 @@ def latency(name, calls):
     return r
 
 
+def mixed(total, steps=2, warm=1):
+    """BASELINE config 5 on one GPU: `total` instances split in thirds over omni4 / diff / tric, one solver and one
+    CUDA stream per model so that the three launch sequences overlap; device-resident inputs"""
+    dev = torch.device("cuda", 0)
+    third = total // 3
+    sizes = {"omni4": total - 2 * third, "diff": third, "tric": third}
+    ctx = {}
+    for name, B in sizes.items():
+        spec = MODELS[name]
+        inst = synth.make_instances(spec, 0, B, device=dev, pose_only=True)
+        ctx[name] = dict(B=B, x0=inst["x0"].t().contiguous(), yref=inst["yref"].permute(1, 2, 0).contiguous(),
+                         s=BatchedRtiSolver(spec, B), st=torch.cuda.Stream(dev),
+                         out=dict(status=torch.empty(B, dtype=torch.int32, device=dev), qp_iter=torch.empty(B, dtype=torch.int32, device=dev)))
+    torch.cuda.synchronize()
+
+    def step():
+        for c in ctx.values():
+            c["s"].reset_async(c["st"])
+            c["s"].solve_device(c["x0"], c["yref"], out=c["out"], stream=c["st"])
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    r = dict(kind="mixed", total=total, sizes=sizes, ms_per_step=ms, solves_per_s=total / ms * 1e3,
+             status_nonzero={n: int((c["out"]["status"] != 0).sum()) for n, c in ctx.items()},
+             mean_qp_iter={n: float(c["out"]["qp_iter"].double().mean()) for n, c in ctx.items()})
+    for c in ctx.values():
+        c["s"].close()
+    return r
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--latency-calls", type=int, default=1000)
     ap.add_argument("--batches", default="diff:65536,diff:131072,tric:65536,omni4:65536,omni4:262144")
+    ap.add_argument("--mixed", type=int, default=0, help="BASELINE config 5: total instances of the mixed omni4/diff/tric batch")
     a = ap.parse_args()
+    if a.mixed:
+        print(json.dumps(mixed(a.mixed)), flush=True)
+        sys.exit(0)
     for item in a.batches.split(","):
         if not item:
             continue
