@@ -344,24 +344,23 @@ struct Grp {
     // hand-over from the per-sweep path: stage k of one instance from its tile (Rec<NV>, lane-resolved pointer,
     // field stride LANES) into a group record.  State right after a factorising sweep: QP data, iterate,
     // factorisation (the steps DZ / DZA / MC / LHD are rewritten before they are read again).
-    NMPC_HD static void tile_to_record(const double* tl, int k, double* rec, int part = 0, int nparts = 1)
+    NMPC_HD static void tile_to_record(const double* tl, int k, double* rec)
     {
         using T = typename S::R;
         const double* lin = tl + T::OFF_LIN + (size_t)k * T::NF_LIN * LANES;
         const double* it = tl + T::OFF_IT + (size_t)k * T::NF_IT * LANES;
         const double* fa = tl + T::OFF_FA + (size_t)k * T::NF_FA * LANES;
-        for (int i = part; i < NZ; i += nparts) rec[R::Q + i] = lin[(T::Q + i) * LANES];
-        for (int i = part; i < NX; i += nparts) rec[R::B0 + i] = lin[(T::B0 + i) * LANES];
-        for (int i = part; i < NB2; i += nparts) { rec[R::DLB + i] = lin[(T::DLB + i) * LANES]; rec[R::DUB + i] = lin[(T::DUB + i) * LANES]; }
-        for (int i = part; i < 3 * NC; i += nparts) rec[R::E + i] = lin[(T::E + i) * LANES];
-        for (int i = part; i < NLU; i += nparts) rec[R::LUU + i] = fa[(T::LUU + i) * LANES];
-        for (int i = part; i < NV * NX; i += nparts) rec[R::KH + i] = fa[(T::KH + i) * LANES];
-        for (int i = part; i < NV; i += nparts) rec[R::LH + i] = fa[(T::LH + i) * LANES];
-        for (int i = part; i < NX; i += nparts) rec[R::RB + i] = fa[(T::RB + i) * LANES];
-        for (int i = part; i < 2 * NB2; i += nparts) { rec[R::T + i] = it[(T::T + i) * LANES]; rec[R::LAM + i] = it[(T::LAM + i) * LANES]; }
-        for (int i = part; i < NZ; i += nparts) rec[R::Z + i] = it[(T::Z + i) * LANES];
-        for (int i = part; i < NX; i += nparts) rec[R::PI + i] = it[(T::PI + i) * LANES];
-        if (part != 0) return;
+        for (int i = 0; i < NZ; i++) rec[R::Q + i] = lin[(T::Q + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::B0 + i] = lin[(T::B0 + i) * LANES];
+        for (int i = 0; i < NB2; i++) { rec[R::DLB + i] = lin[(T::DLB + i) * LANES]; rec[R::DUB + i] = lin[(T::DUB + i) * LANES]; }
+        for (int i = 0; i < 3 * NC; i++) rec[R::E + i] = lin[(T::E + i) * LANES];
+        for (int i = 0; i < NLU; i++) rec[R::LUU + i] = fa[(T::LUU + i) * LANES];
+        for (int i = 0; i < NV * NX; i++) rec[R::KH + i] = fa[(T::KH + i) * LANES];
+        for (int i = 0; i < NV; i++) rec[R::LH + i] = fa[(T::LH + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::RB + i] = fa[(T::RB + i) * LANES];
+        for (int i = 0; i < 2 * NB2; i++) { rec[R::T + i] = it[(T::T + i) * LANES]; rec[R::LAM + i] = it[(T::LAM + i) * LANES]; }
+        for (int i = 0; i < NZ; i++) rec[R::Z + i] = it[(T::Z + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::PI + i] = it[(T::PI + i) * LANES];
         // padding and the step fields stay defined (the steps are rewritten before they are read)
         if ((3 * NC) & 1) rec[R::E + 3 * NC] = 0.0;
         if (NLU & 1) rec[R::LUU + NLU] = 0.0;

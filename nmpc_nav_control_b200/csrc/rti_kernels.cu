@@ -328,20 +328,19 @@ __global__ void k_handover_assign(int nchunk, int ldc, const double* __restrict_
     c.done = 0;
     reinterpret_cast<typename S::LaneCtl*>(ctl_out)[q] = c;
 }
-// state of the unfinished instances from the tile layout into their group records; block = one tile x CV_PARTS field
-// slices (more loads in flight per instance), grid (tiles, stages); a tile without unfinished lanes returns at once
-constexpr int CV_PARTS = 4;
+// state of the unfinished instances from the tile layout into their group records; grid (instances, stages).
+// (A variant with four field slices per instance and one block per tile was slower: 3.0 ms against 2.0 ms.)
 template <class M, int G>
-__global__ void __launch_bounds__(LANES * CV_PARTS)
+__global__ void __launch_bounds__(128)
 k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp)
 {
     using GP = Grp<M, G>;
     using R = typename Rti<M>::R;
-    const int li = blockIdx.x * LANES + threadIdx.x, k = blockIdx.y;
+    const int li = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
     if (li >= nchunk) return;
     const int q = map[li];
     if (q < 0) return;
-    GP::tile_to_record(ws_tile + (size_t)blockIdx.x * R::tile_doubles + threadIdx.x, k, GP::rec_of(ws_grp, q, k), threadIdx.y, CV_PARTS);
+    GP::tile_to_record(ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES), k, GP::rec_of(ws_grp, q, k));
 }
 // K4 for the hybrid schedule: the step of an instance comes from its tile or, if it was handed over, from its group record
 template <class M>
@@ -909,10 +908,10 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 int* bcnt = s->d_cnt + s->cnt_cap - 2 - 2 * HB_NB;      // zeroed with the counters at the start of the chunk
                 k_handover_count<<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, s->d_map);
                 k_handover_assign<M><<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, nres, s->d_list, s->d_map, s->d_ctl_g);
-                dim3 gc((n + LANES - 1) / LANES, NSTAGE + 1), bc(LANES, CV_PARTS);
-                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, bc, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
-                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, bc, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
-                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, bc, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                dim3 gc((n + 127) / 128, NSTAGE + 1);
+                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
                 const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
                 rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nres, s->d_list, s->d_ctl_g}, st);
                 if (rc) return rc;
