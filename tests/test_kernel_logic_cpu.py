@@ -37,6 +37,19 @@ def test_group_slot_refill_and_other_group_sizes(oracle_mod):
         assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, (name, G)
 
 
+@pytest.mark.parametrize("name,K,B", [("diff", 0, 40), ("diff", 5, 48), ("diff", 8, 64), ("tric", 4, 40), ("omni4", 9, 24)])
+def test_hybrid_handover(oracle_mod, name, K, B):
+    """the hybrid schedule: K iterations of the per-lane sweeps (a lane whose corrector overshoots leaves them at its
+    centering repeat), record conversion, then the lane-group kernel resumes the unfinished instances in the middle of
+    their iteration"""
+    spec, x0, yref, _ = instances(name, 1200, B)
+    ref = oracle_solve(oracle_mod, name, x0, yref)
+    out = emul.emul_rti(name, x0, yref, hybrid=K)
+    assert 0 < out["resumed"] <= B
+    assert (out["qp_status"] == 0).all() and (out["qp_iter"] == ref["qp_iter"]).all()
+    assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0
+
+
 @pytest.mark.parametrize("group", [True, False])
 @pytest.mark.parametrize("name", ["diff", "omni4", "tric"])
 def test_warm_steps_and_pose_only_yref(oracle_mod, name, group):
