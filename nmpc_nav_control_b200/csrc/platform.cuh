@@ -27,7 +27,10 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 // per-lane scratch columns live in shared memory on the device, interleaved over the threads of a
 // sweep CTA (bank-conflict free); the host emulation uses a plain array
 #if defined(__CUDACC__)
-#define NMPC_SCRATCH_STRIDE 64
+#ifndef NMPC_SW_TILES
+#define NMPC_SW_TILES 1                 // tiles (warps) per CTA of a sweep kernel (1: the omni4 factorising sweep fits more warps per SM)
+#endif
+#define NMPC_SCRATCH_STRIDE (32 * NMPC_SW_TILES)
 #else
 #define NMPC_SCRATCH_STRIDE 1
 #endif

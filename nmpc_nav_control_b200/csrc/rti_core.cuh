@@ -428,12 +428,13 @@ struct Rti {
     // ---- B sweep: (apply previous step) + residuals + Riccati factorisation, stage N..0 -----
     // All vectors and matrices carried from stage to stage live in a per-lane scratch column `sc`
     // (shared memory on the device, element stride PSTRIDE; a plain array in the host emulation):
-    // the cost-to-go matrix P (packed symmetric, double-buffered because the Schur complement of a
-    // stage reads all of the successor's P), its gradient pv, and the three vectors of the
+    // the cost-to-go matrix P (packed symmetric, ONE buffer: [A B] is upper triangular in the state order
+    // x, y, theta, actual, ref, so entry (i, j) of A'PA only reads P(k, l) with k <= i, l <= j and the
+    // congruence can overwrite P column by column from the last one), its gradient pv, and the three vectors of the
     // update / adjoint recursion.  Registers only carry the norm accumulators.  The stage body is
     // cut in two phases (update + residuals, then Riccati) so that neither holds the other's data.
     struct CarryB {
-        static constexpr int SC_P = 0, SC_PV = 2 * NPK, SC_PIO = SC_PV + NX, SC_DPI = SC_PIO + NX, SC_XN = SC_DPI + NX,
+        static constexpr int SC_P = 0, SC_PV = NPK, SC_PIO = SC_PV + NX, SC_DPI = SC_PIO + NX, SC_XN = SC_DPI + NX,
                              SC_N = SC_XN + NX;
         double* sc;
         int cur;          // which P buffer holds the successor's cost-to-go
@@ -660,8 +661,8 @@ struct Rti {
         using C = CarryB;
         const bool hasU = k < NSTAGE, hasX = k > 0;
         double* sc = cy.sc;
-        const double* P = sc + (size_t)(C::SC_P + cy.cur * NPK) * PSTRIDE;         // successor's cost-to-go
-        double* Pn = sc + (size_t)(C::SC_P + (cy.cur ^ 1) * NPK) * PSTRIDE;        // this stage's
+        const double* P = sc + (size_t)C::SC_P * PSTRIDE;         // successor's cost-to-go ...
+        double* Pn = sc + (size_t)C::SC_P * PSTRIDE;              // ... overwritten in place by this stage's
         if (hasU) {
             L lin;
             load_lin(in.lin, tb.lti + k * 4 * NV, lin);
@@ -739,8 +740,9 @@ struct Rti {
                         out.fa[(R::KH + a * NX + j) * LANES] = Kh[a][j];
                     }
                 }
+                // last column first: column j reads only columns <= j of the successor's P (see CarryB)
 #pragma unroll
-                for (int j = 0; j < NX; j++) {
+                for (int j = NX - 1; j >= 0; j--) {
                     double g[NX], cu[NV], cx[NX];
                     P_col_s(P, lin, NV + j, g);
                     apply_T(lin, g, cu, cx);
@@ -769,7 +771,6 @@ struct Rti {
                 sc[(C::SC_PV + i) * PSTRIDE] = gx[i];
             }
         }
-        cy.cur ^= 1;
     }
 
     NMPC_HD static void stage_B(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,

@@ -109,7 +109,7 @@ k_linearize(int B, int i0, int nchunk, const double* __restrict__ x0bar, const d
 // and per-iteration counters.  ctl_d rows: nrm[4], mu, alpha, sigmu, mu_aff0, lin_res, mcw;
 // ctl_i rows: done, iter, status, fb, nfb.
 constexpr int NCTL_D = 10, NCTL_I = 5;
-constexpr int SW_TILES = 2;            // tiles (warps) per CTA of a sweep kernel
+constexpr int SW_TILES = NMPC_SW_TILES;  // tiles (warps) per CTA of a sweep kernel
 static_assert(LANES * SW_TILES == NMPC_SCRATCH_STRIDE, "scratch columns are interleaved over the CTA's threads");
 
 template <class S>
@@ -139,7 +139,7 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
 //   gate: number of lanes still iterating (act[it]); 0 -> the whole grid returns at once.
 //   cnt_out (B kernels): lanes that continue -> act[it+1].
 template <class M, int KIND>
-__global__ void __launch_bounds__(LANES * SW_TILES, KIND == 5 ? 8 : 4)
+__global__ void __launch_bounds__(LANES * SW_TILES, (KIND == 5 ? 16 : 8) / SW_TILES)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
         double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min,
         int defer_fb)
