@@ -7,3 +7,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_sweep --launch-skip 1 --launch-count 2 -o gpurun_out/sweeps_full python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_sw.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_ipm_group -c 1 -o gpurun_out/grp_resume_full python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_grp.log 2>&1
 ls -la gpurun_out
+timeout 1200 python tools/bench_models.py --latency-calls 1000 > gpurun_out/models_final.jsonl 2> gpurun_out/models_final.err
+timeout 1200 python tools/bench_models.py --mixed 1048576 >> gpurun_out/models_final.jsonl 2>> gpurun_out/models_final.err
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio --clock-control none -k regex:^k_ -c 45 --csv --log-file gpurun_out/launches_omni4.csv python tools/bench_models.py --latency-calls 1 --batches omni4:65536 > gpurun_out/ncu_omni.log 2>&1
