@@ -1,0 +1,62 @@
+"""Every K3 schedule (per-sweep kernels, lane-group kernel, hybrid) and the chunked path give the same answer:
+same QP iteration counts, iterates within the parity tolerance of each other and of the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+_CHILD = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from nmpc_nav_control_b200 import synth
+from nmpc_nav_control_b200.problem import MODELS
+from nmpc_nav_control_b200.solver import BatchedRtiSolver
+name, B, out = sys.argv[2], int(sys.argv[3]), sys.argv[4]
+spec = MODELS[name]
+inst = synth.make_instances(spec, 31, B, device="cuda", pose_only=True)
+x0 = inst["x0"].t().contiguous(); yref = inst["yref"].permute(1, 2, 0).contiguous()
+s = BatchedRtiSolver(spec, B)
+s.reset()
+r = s.solve_device(x0, yref)
+torch.cuda.synchronize()
+x, u = s.get_iterate(B)
+np.savez(out, x=x, u=u, it=r["qp_iter"].cpu().numpy(), st=r["status"].cpu().numpy())
+'''
+
+
+def _run(tmp_path, name, B, tag, env):
+    out = str(tmp_path / f"{name}_{tag}.npz")
+    e = dict(os.environ); e.update(env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", _CHILD, root, name, str(B), out], check=True, env=e)   # the schedule is read at create time
+    return np.load(out)
+
+
+@pytest.mark.parametrize("name,B", [("diff", 6000), ("omni4", 1500), ("tric", 5000)])
+def test_schedules_and_chunking_agree(tmp_path, oracle_mod, name, B):
+    from helpers import instances, oracle_solve, parity_report
+    runs = {
+        "sweep": {"NMPC_K3": "sweep"},
+        "group": {"NMPC_K3": "group"},
+        "hybrid": {"NMPC_K3": "hybrid", "NMPC_HYB_MIN": "0"},
+        "hybrid_chunked": {"NMPC_K3": "hybrid", "NMPC_HYB_MIN": "0", "NMPC_CHUNK": "2048"},     # last chunk is ragged
+        "group_chunked": {"NMPC_K3": "group", "NMPC_CHUNK": "1024"},
+    }
+    res = {k: _run(tmp_path, name, B, k, v) for k, v in runs.items()}
+    base = res["sweep"]
+    assert (base["st"] == 0).all()
+    for k, r in res.items():
+        assert (r["st"] == 0).all(), k
+        assert np.array_equal(r["it"], base["it"]), k
+        assert parity_report(r["x"], base["x"])[0] == 0 and parity_report(r["u"], base["u"])[0] == 0, k
+    # and against the oracle on a slice (same generator, instance index = global index)
+    n = 256
+    spec, x0, yref, _ = instances(name, 31, n, pose_only=True)
+    yfull = np.zeros((n, spec.n + 1, spec.ny)); yfull[:, :, :3] = yref
+    ref = oracle_solve(oracle_mod, name, x0, yfull)
+    assert (ref["qp_iter"] == base["it"][:n]).all()
+    assert parity_report(res["hybrid"]["x"][:n], ref["x"])[0] == 0 and parity_report(res["hybrid"]["u"][:n], ref["u"])[0] == 0
