@@ -217,17 +217,20 @@ struct Grp {
     static constexpr int O_IN = 0;
     static constexpr int RING = imax(imax(imax(Img<SW_B>::D * Img<SW_B>::SIZE, Img<SW_F>::D * Img<SW_F>::SIZE),
                                           imax(Img<SW_BD>::D * Img<SW_BD>::SIZE, Img<SW_FD>::D * Img<SW_FD>::SIZE)),
-                                     G * 8 /* the end-of-sweep reductions borrow the ring */);
-    static constexpr int DMAX = imax(imax(Img<SW_B>::D, Img<SW_F>::D), imax(Img<SW_BD>::D, Img<SW_FD>::D));
+                                     imax(G * 8 /* the end-of-sweep reductions borrow the ring */,
+                                          3 * Img<SW_B>::SIZE /* the B sweep keeps the stages of its two halves and the prefetch */));
+    static constexpr int DMAX = imax(3, imax(imax(Img<SW_B>::D, Img<SW_F>::D), imax(Img<SW_BD>::D, Img<SW_FD>::D)));
     static constexpr int O_CAR = O_IN + RING;             // [2][3][NX] carries of the B sweep: pio, dpi, xn
                                                           //   (F: dx [2][NX]; Bd: dp [2][NX])
     static constexpr int O_PV = O_CAR + 6 * NX;           // NX   gradient of the cost-to-go
-    static constexpr int O_RB = O_PV + NX;                // NX   dynamics residual
-    static constexpr int O_GX = O_RB + NX;                // NX   stage gradient, state rows
-    static constexpr int O_DGX = O_GX + NX;               // NX   diagonal H + reg + Gamma, state rows
-    static constexpr int O_GU = O_DGX + NX;               // NV   control gradient / F: s_a / Bd: q_u
-    static constexpr int O_DGU = O_GU + NV;               // NV
-    static constexpr int O_CB = O_DGU + NV;               // [NCT+1][4] per-constraint terms (last entry: zeros)
+    // hand-off of the B sweep's update half (stage k) to its Riccati half (one super-step later): two buffers each
+    static constexpr int O_RB = O_PV + NX;                // [2][NX] dynamics residual
+    static constexpr int O_GX = O_RB + 2 * NX;            // [2][NX] stage gradient, state rows (Bd: q_x)
+    static constexpr int O_DGX = O_GX + 2 * NX;           // [2][NX] diagonal H + reg + Gamma, state rows
+    static constexpr int O_GU = O_DGX + 2 * NX;           // [2][NV] control gradient (F: s_a, Bd: q_u)
+    static constexpr int O_DGU = O_GU + 2 * NV;           // [2][NV]
+    static constexpr int O_GG = O_DGU + 2 * NV;           // NV   control gradient with the cost-to-go terms (B4 -> B5)
+    static constexpr int O_CB = O_GG + NV;                // [NCT+1][4] per-constraint terms (last entry: zeros)
     static constexpr int O_PBA = O_CB + 4 * (NCT + 1);    // [NX][NZ]  P * [A B], columns [x; u]
     static constexpr int O_MUU = O_PBA + NX * NZ;         // [NV][NV]
     static constexpr int O_KB = O_MUU + NV * NV;          // [NV][NX]
@@ -288,6 +291,8 @@ struct Grp {
         int cq_i1, cq_i2, cq_k1, cq_k2;   // LTI part of the column of J: k1 * v[i1] + k2 * v[i2], k from the lte table
         // constraint role (c = r < NCT)
         int ct_z, ct_x, ct_u;     // z-order index of the bounded component; its state index or -1; its control index or -1
+        // column role (state j = r < NX): column j of J = pose part (E column cs_e, -1: unit vector e_j) + LTI part
+        int cs_e, cs_i1, cs_i2, cs_k1, cs_k2;
         double ct_s;              // +1 lower, -1 upper
         // B sweep
         double Pc[NX];            // column r of the cost-to-go of the successor stage
@@ -336,6 +341,11 @@ struct Grp {
         L.ct_u = b < NV ? b : -1;
         L.ct_x = b < NV ? -1 : 3 + b;
         L.ct_z = b < NV ? b : NU + 3 + b;
+        L.cs_e = -1; L.cs_i1 = 0; L.cs_i2 = 0; L.cs_k1 = LT_ZERO; L.cs_k2 = LT_ZERO;
+        if (r == 2) L.cs_e = 0;
+        else if (r >= 3 && r < 3 + NV) { const int c = r - 3; L.cs_e = 1 + c; L.cs_i1 = 3 + c; L.cs_k1 = c; }
+        else if (r >= 3 + NV && r < NX) { const int c = r - 3 - NV; L.cs_e = 1 + NV + c; L.cs_i1 = 3 + c; L.cs_k1 = NV + c; L.cs_i2 = 3 + NV + c; L.cs_k2 = LT_ONE; }
+        L.cs_e = grp_pin(L.cs_e); L.cs_i1 = grp_pin(L.cs_i1); L.cs_i2 = grp_pin(L.cs_i2); L.cs_k1 = grp_pin(L.cs_k1); L.cs_k2 = grp_pin(L.cs_k2);
         L.cq_z = grp_pin(L.cq_z); L.cq_x = grp_pin(L.cq_x); L.cq_y = grp_pin(L.cq_y); L.cq_bl = grp_pin(L.cq_bl); L.cq_bu = grp_pin(L.cq_bu);
         L.cq_i1 = grp_pin(L.cq_i1); L.cq_i2 = grp_pin(L.cq_i2); L.cq_k1 = grp_pin(L.cq_k1); L.cq_k2 = grp_pin(L.cq_k2);
         L.ct_z = grp_pin(L.ct_z); L.ct_x = grp_pin(L.ct_x); L.ct_u = grp_pin(L.ct_u);
@@ -474,46 +484,54 @@ struct Grp {
     // =========================================================================================
     NMPC_HD static void sweep_B(Lane* lanes, double* sm, double* ws, const Tables& tb, const IpmOpts& o)
     {
+        // The sweep is two recursions that only meet in the stage gradient: the UPDATE half of stage k (step, multipliers,
+        // residuals: needs the update half of stage k+1) and the RICCATI half (needs the Riccati half of stage k+1 and the
+        // update half of stage k).  They run skewed by one stage: super-step t does update(N - t) and riccati(N - t + 1) in
+        // the same phases, which shortens the dependent chain of a stage by a third and saves one phase boundary.
+        constexpr int ISZ = Img<SW_B>::SIZE;
         GRP_PHASE_BEGIN(lanes)
             L.ng = L.nb = L.nd = L.nm = L.musum = L.lru = 0.0;
+            L.tsrc = grp_pin_ptr(tb.stg + (size_t)(NSTAGE + 1) * TROW + 2 * L.wl);      // one stage before the first (N)
             if (L.run) {
                 double* scr = sm + L.so;
                 if (L.r < NX) { scr[O_CAR + L.r] = 0.0; scr[O_CAR + NX + L.r] = 0.0; scr[O_CAR + 2 * NX + L.r] = 0.0; scr[O_PV + L.r] = 0.0; }
                 if (L.r < 4) scr[O_CB + 4 * NCT + L.r] = 0.0;
+                L.grec = grp_pin_ptr(rec_of(ws, L.li, NSTAGE) + R::NREC);
             }
-            begin_sweep<SW_B, -1>(L, sm, ws, tb, NSTAGE);
+            prefetch<SW_B, -1>(L, sm, 1, 0, true);
         GRP_PHASE_END
 #pragma unroll 1
-        for (int s = 0; s <= NSTAGE; s++) {
-            constexpr int D = Img<SW_B>::D;
-            const int k = NSTAGE - s, slot = s % D, pslot = (s + D - 1) % D;
-            const bool hasU = k < NSTAGE, hasX = k > 0, pvalid = s + D - 1 <= NSTAGE;
+        for (int t = 0; t <= NSTAGE + 1; t++) {
+            const int ku = NSTAGE - t, kr = ku + 1;
+            const bool Uv = t <= NSTAGE, Rv = t >= 1;
+            const bool hasU_u = ku < NSTAGE, hasX_u = ku > 0, hasU_r = kr < NSTAGE, hasX_r = kr > 0;
+            const int slot_u = t % 3, slot_r = (t + 2) % 3, pslot = (t + 1) % 3, par_u = t & 1, par_r = par_u ^ 1;
             GRP_PHASE_BEGIN(lanes)
-                begin_stage<SW_B, -1>(L);
+                if (Uv) { L.grec -= R::NREC; L.tsrc -= TROW; }
+                grp_cp_wait<0>();
             GRP_PHASE_END
-            // ---- B1a: prefetch the next stage; one constraint per lane; row r of P * [A B] ----------
+            // ---- P1: prefetch; update(ku): one constraint per lane;  riccati(kr): row r of P * [A B] ----------------
             GRP_PHASE_BEGIN(lanes)
-                prefetch<SW_B, -1>(L, sm, D - 1, pslot, pvalid);
+                prefetch<SW_B, -1>(L, sm, 1, pslot, Uv && ku > 0);
                 if (!L.run) continue;
-                const double* ltk = sm + L.to + slot * TROW;
                 double* scr = sm + L.so;
-                double* grec = L.grec;
-                const double* img = scr + O_IN + slot * Img<SW_B>::SIZE;
-                const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
-                const double a_step = L.astep;
-                if (L.r < NCT) {
+                if (Uv && L.r < NCT) {
+                    double* grec = L.grec;
+                    const double* img = scr + O_IN + slot_u * ISZ;
+                    const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
+                    const double a_step = L.astep;
                     const int c = L.r;
-                    const bool actc = (L.ct_u >= 0) ? hasU : hasX;
+                    const bool actc = (L.ct_u >= 0) ? hasU_u : hasX_u;
                     double rpart = 0.0, lpart = 0.0, gpart = 0.0, Gp = 0.0;
                     if (actc) {
                         const double sg = L.ct_s;
                         const double dbd = rec[R::DLB + c], z = rec2[R::Z + L.ct_z], dz = rec2[R::DZ + L.ct_z];
-                        const double lam = rec2[R::LAM + c], t = rec2[R::T + c], mc = rec2[R::MC + c];
-                        const double rd = sg * (dbd - z) + t;
-                        const double rm = lam * t - o.tau_min + L.mcw * mc - L.sigmu;
+                        const double lam = rec2[R::LAM + c], tt = rec2[R::T + c], mc = rec2[R::MC + c];
+                        const double rd = sg * (dbd - z) + tt;
+                        const double rm = lam * tt - o.tau_min + L.mcw * mc - L.sigmu;
                         const double dt = sg * dz - rd;
-                        const double dlam = -(lam * dt + rm) / t;
-                        const double lam_n = lam + a_step * dlam, t_n = t + a_step * dt, zn = z + a_step * dz;
+                        const double dlam = -(lam * dt + rm) / tt;
+                        const double lam_n = lam + a_step * dlam, t_n = tt + a_step * dt, zn = z + a_step * dz;
                         rpart = -sg * (lam + dlam);
                         const double rd_n = sg * (dbd - zn) + t_n;
                         const double pm = lam_n * t_n;
@@ -530,149 +548,159 @@ struct Grp {
                     }
                     scr[O_CB + 4 * c] = rpart; scr[O_CB + 4 * c + 1] = lpart; scr[O_CB + 4 * c + 2] = gpart; scr[O_CB + 4 * c + 3] = Gp;
                 }
-                if (hasU) {
+                if (Rv && hasU_r) {
+                    const double* recr = Img<SW_B>::a(scr + O_IN + slot_r * ISZ);
+                    const double* ltr = sm + L.to + slot_r * TROW;
 #pragma unroll
-                    for (int i = 0; i < 3 * NC; i++) L.Ef[i] = rec[R::E + i];
+                    for (int i = 0; i < 3 * NC; i++) L.Ef[i] = recr[R::E + i];
 #pragma unroll
-                    for (int i = 0; i < 4 * NV; i++) L.lt[i] = ltk[i];
+                    for (int i = 0; i < 4 * NV; i++) L.lt[i] = ltr[i];
                     if (L.r < NX) {
 #pragma unroll
                         for (int w = 0; w < NZ; w++)
-                            if (hasX || w >= NX) scr[O_PBA + L.r * NZ + w] = jcol_dot_r(w, L.Pc, L.Ef, L.lt);
+                            if (hasX_r || w >= NX) scr[O_PBA + L.r * NZ + w] = jcol_dot_r(w, L.Pc, L.Ef, L.lt);
                     }
                 }
             GRP_PHASE_END
-            // ---- B1b: one component per lane: step, stationarity residual, multiplier step; row r of
-            //      the dynamics residual --------------------------------------------------------------
+            // ---- P2: update(ku): one component per lane, row r of the dynamics residual;
+            //      riccati(kr): column of M = J'PJ + D, gradient += J'(P rb + p) ------------------------------------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                double* grec = L.grec;
-                const double* img = scr + O_IN + slot * Img<SW_B>::SIZE;
-                const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
-                const double* car = scr + O_CAR + (s & 1) * 3 * NX;          // from stage k+1: pio | dpi | xn
-                double* carn = scr + O_CAR + ((s & 1) ^ 1) * 3 * NX;
-                const double* ltk = sm + L.to + slot * TROW;
-                const double a_step = L.astep;
-                if (L.r < NC) {
-                    // generic component: column q = r of the pose rows E
-                    const int q = L.r;
-                    const bool isx = L.cq_x >= 0;
-                    const bool has = isx ? hasX : hasU;
-                    const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
-                    const double k1 = ltk[L.cq_k1], k2 = ltk[L.cq_k2];
-                    const double v1 = jt_comp(L, e0, e1, e2, k1, k2, car);
-                    const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
-                    const double v3 = jt_comp(L, e0, e1, e2, k1, k2, scr + O_PV);
-                    const double H = hasU ? tb.dt * ltk[T_W + L.cq_y] : L.We_c;
-                    const double qv = rec[R::Q + L.cq_z], z = rec2[R::Z + L.cq_z], dz = rec2[R::DZ + L.cq_z];
-                    const bool haspi = isx && hasX;
-                    const double pin = haspi ? rec2[R::PI + (isx ? L.cq_x : 0)] : 0.0;
-                    const double* cl = scr + O_CB + 4 * L.cq_bl;
-                    const double* cu = scr + O_CB + 4 * L.cq_bu;
-                    double r = qv + H * z - pin + v1 + H * dz + v2;
-                    r += cl[0] + cu[0];
-                    const double pin_n = haspi ? pin + a_step * r : 0.0;
-                    const double zn = z + a_step * dz;
-                    double g = qv + H * zn - pin_n + (v1 + a_step * v2);
-                    g += cl[1] + cu[1];
-                    if (has) L.ng = grp_maxabs(L.ng, g);
-                    if (!isx && hasU) L.lru = grp_maxabs(L.lru, r);
-                    g += cl[2] + cu[2];
-                    g += v3;
-                    const double dg = H + o.reg_prim + (cl[3] + cu[3]);
-                    grec[R::Z + L.cq_z] = zn;
-                    if (isx) {
-                        const int j = L.cq_x;
+                if (Uv) {
+                    double* grec = L.grec;
+                    const double* img = scr + O_IN + slot_u * ISZ;
+                    const double* rec = Img<SW_B>::a(img); const double* rec2 = Img<SW_B>::b(img);
+                    const double* car = scr + O_CAR + par_u * 3 * NX;           // from stage ku+1: pio | dpi | xn
+                    double* carn = scr + O_CAR + par_r * 3 * NX;
+                    const double* ltk = sm + L.to + slot_u * TROW;
+                    const double a_step = L.astep;
+                    if (L.r < NC) {
+                        // generic component: column q = r of the pose rows E
+                        const int q = L.r;
+                        const bool isx = L.cq_x >= 0;
+                        const bool has = isx ? hasX_u : hasU_u;
+                        const double e0 = rec[R::E + q], e1 = rec[R::E + NC + q], e2 = rec[R::E + 2 * NC + q];
+                        const double k1 = ltk[L.cq_k1], k2 = ltk[L.cq_k2];
+                        const double v1 = jt_comp(L, e0, e1, e2, k1, k2, car);
+                        const double v2 = jt_comp(L, e0, e1, e2, k1, k2, car + NX);
+                        const double H = hasU_u ? tb.dt * ltk[T_W + L.cq_y] : L.We_c;
+                        const double qv = rec[R::Q + L.cq_z], z = rec2[R::Z + L.cq_z], dz = rec2[R::DZ + L.cq_z];
+                        const bool haspi = isx && hasX_u;
+                        const double pin = haspi ? rec2[R::PI + (isx ? L.cq_x : 0)] : 0.0;
+                        const double* cl = scr + O_CB + 4 * L.cq_bl;
+                        const double* cu = scr + O_CB + 4 * L.cq_bu;
+                        double r = qv + H * z - pin + v1 + H * dz + v2;
+                        r += cl[0] + cu[0];
+                        const double pin_n = haspi ? pin + a_step * r : 0.0;
+                        const double zn = z + a_step * dz;
+                        double g = qv + H * zn - pin_n + (v1 + a_step * v2);
+                        g += cl[1] + cu[1];
+                        if (has) L.ng = grp_maxabs(L.ng, g);
+                        if (!isx && hasU_u) L.lru = grp_maxabs(L.lru, r);
+                        g += cl[2] + cu[2];
+                        const double dg = H + o.reg_prim + (cl[3] + cu[3]);
+                        grec[R::Z + L.cq_z] = zn;
+                        if (isx) {
+                            const int j = L.cq_x;
+                            grec[R::PI + j] = pin_n;
+                            carn[j] = pin; carn[NX + j] = haspi ? r : 0.0; carn[2 * NX + j] = zn;
+                            scr[O_GX + par_u * NX + j] = g; scr[O_DGX + par_u * NX + j] = dg;
+                        } else {
+                            scr[O_GU + par_u * NV + L.cq_z] = g; scr[O_DGU + par_u * NV + L.cq_z] = dg;
+                        }
+                    }
+                    if (L.r == XL || L.r == YL) {
+                        // pose components x, y: unit columns of J, no bounds
+                        const int j = L.r == XL ? 0 : 1;
+                        const double v1 = car[j], v2 = car[NX + j];              // zero at the terminal stage
+                        const double H = hasU_u ? tb.dt * ltk[T_W + j] : L.We_xy;
+                        const double qv = rec[R::Q + NU + j], z = rec2[R::Z + NU + j], dz = rec2[R::DZ + NU + j];
+                        const double pin = hasX_u ? rec2[R::PI + j] : 0.0;
+                        const double r = qv + H * z - pin + v1 + H * dz + v2;
+                        const double pin_n = hasX_u ? pin + a_step * r : 0.0;
+                        const double zn = z + a_step * dz;
+                        const double g = qv + H * zn - pin_n + (v1 + a_step * v2);
+                        if (hasX_u) L.ng = grp_maxabs(L.ng, g);
+                        grec[R::Z + NU + j] = zn;
                         grec[R::PI + j] = pin_n;
-                        carn[j] = pin; carn[NX + j] = haspi ? r : 0.0; carn[2 * NX + j] = zn;
-                        scr[O_GX + j] = g; scr[O_DGX + j] = dg;
-                    } else {
-                        scr[O_GU + L.cq_z] = g; scr[O_DGU + L.cq_z] = dg;
+                        carn[j] = pin; carn[NX + j] = hasX_u ? r : 0.0; carn[2 * NX + j] = zn;
+                        scr[O_GX + par_u * NX + j] = g; scr[O_DGX + par_u * NX + j] = H + o.reg_prim;
+                    }
+                    if (hasU_u && L.r < NX) {
+                        // dynamics residual, row r, at the new iterate (recomputed from the record: no exchange)
+                        const double rb = jrow(L.r, [&](int c) { return rec2[R::Z + c] + a_step * rec2[R::DZ + c]; },
+                                               [&](int j) { return rec2[R::Z + NU + j] + a_step * rec2[R::DZ + NU + j]; }, rec + R::E, ltk)
+                                          + rec[R::B0 + L.r] - car[2 * NX + L.r];
+                        L.nb = grp_maxabs(L.nb, rb);
+                        scr[O_RB + par_u * NX + L.r] = rb;
+                        grec[R::RB + L.r] = rb;
                     }
                 }
-                if (L.r == XL || L.r == YL) {
-                    // pose components x, y: unit columns of J, no bounds
-                    const int j = L.r == XL ? 0 : 1;
-                    const double v1 = car[j], v2 = car[NX + j], v3 = scr[O_PV + j];      // all zero at the terminal stage
-                    const double H = hasU ? tb.dt * ltk[T_W + j] : L.We_xy;
-                    const double qv = rec[R::Q + NU + j], z = rec2[R::Z + NU + j], dz = rec2[R::DZ + NU + j];
-                    const double pin = hasX ? rec2[R::PI + j] : 0.0;
-                    const double r = qv + H * z - pin + v1 + H * dz + v2;
-                    const double pin_n = hasX ? pin + a_step * r : 0.0;
-                    const double zn = z + a_step * dz;
-                    double g = qv + H * zn - pin_n + (v1 + a_step * v2);
-                    if (hasX) L.ng = grp_maxabs(L.ng, g);
-                    g += v3;
-                    grec[R::Z + NU + j] = zn;
-                    grec[R::PI + j] = pin_n;
-                    carn[j] = pin; carn[NX + j] = hasX ? r : 0.0; carn[2 * NX + j] = zn;
-                    scr[O_GX + j] = g; scr[O_DGX + j] = H + o.reg_prim;
+                if (Rv && !hasU_r) {
+                    // terminal stage: P = diag(We + reg + Gamma), p = g
+                    if (L.r < NX) {
+                        const double pd = scr[O_DGX + par_r * NX + L.r];
+#pragma unroll
+                        for (int i = 0; i < NX; i++) L.Pc[i] = pd * sel(i == L.r);
+                        scr[O_PV + L.r] = scr[O_GX + par_r * NX + L.r];
+                    }
                 }
-                if (hasU && L.r < NX) {
-                    // dynamics residual, row r, at the new iterate (recomputed from the record: no exchange)
-                    const double rb = jrow(L.r, [&](int c) { return rec2[R::Z + c] + a_step * rec2[R::DZ + c]; },
-                                           [&](int j) { return rec2[R::Z + NU + j] + a_step * rec2[R::DZ + NU + j]; }, rec + R::E, ltk)
-                                      + rec[R::B0 + L.r] - car[2 * NX + L.r];
-                    L.nb = grp_maxabs(L.nb, rb);
-                    scr[O_RB + L.r] = rb;
-                    grec[R::RB + L.r] = rb;
-                }
-            GRP_PHASE_END
-            if (!hasU) {
-                // terminal stage: P = diag(We + reg + Gamma), p = g
-                GRP_PHASE_BEGIN(lanes)
-                    if (!L.run || L.r >= NX) continue;
-                    double* scr = sm + L.so;
-                    const double pd = scr[O_DGX + L.r];
+                if (Rv && hasU_r) {
+                    const double* recr = Img<SW_B>::a(scr + O_IN + slot_r * ISZ);
+                    const double* ltr = sm + L.to + slot_r * TROW;
+                    double rbv[NX], pvv[NX];
 #pragma unroll
-                    for (int i = 0; i < NX; i++) L.Pc[i] = pd * sel(i == L.r);
-                    scr[O_PV + L.r] = scr[O_GX + L.r];
-                GRP_PHASE_END
-                continue;
-            }
-            // ---- B4: column of M = J'PJ + D; gradient += J'P rb ------------------------------------
-            GRP_PHASE_BEGIN(lanes)
-                if (!L.run) continue;
-                double* scr = sm + L.so;
-                double rbv[NX];
-#pragma unroll
-                for (int i = 0; i < NX; i++) rbv[i] = scr[O_RB + i];
-                if (hasX && L.r < NX) {
-                    double col[NX];
-#pragma unroll
-                    for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + L.r];
-                    double gg = scr[O_GX + L.r];
-#pragma unroll
-                    for (int i = 0; i < NX; i++) gg += col[i] * rbv[i];
-                    L.gx = gg;
-                    const double dg = scr[O_DGX + L.r];
-#pragma unroll
-                    for (int wp = 0; wp < NZ; wp++) L.Mx[wp] = jcol_dot_r(wp, col, L.Ef, L.lt) + (wp < NX ? dg * sel(wp == L.r) : 0.0);
-                }
-                if (L.r >= ULB && L.r < ULB + ULN) {
-#pragma unroll
-                    for (int e = 0; e < NV / ULN; e++) {
-                        const int a = (L.r - ULB) * (NV / ULN) + e;
+                    for (int i = 0; i < NX; i++) { rbv[i] = scr[O_RB + par_r * NX + i]; pvv[i] = scr[O_PV + i]; }
+                    if (hasX_r && L.r < NX) {
                         double col[NX];
 #pragma unroll
-                        for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + NX + a];
-                        double gg = scr[O_GU + a];
+                        for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + L.r];
+                        // (J' p)_r with the lane's column role
+                        const bool unit = L.cs_e < 0;
+                        const int ce = unit ? 0 : L.cs_e;
+                        const double e0 = unit ? sel(L.r == 0) : recr[R::E + ce], e1 = unit ? sel(L.r == 1) : recr[R::E + NC + ce],
+                                     e2 = unit ? 0.0 : recr[R::E + 2 * NC + ce];
+                        double gg = scr[O_GX + par_r * NX + L.r] + (e0 * pvv[0] + e1 * pvv[1] + e2 * pvv[2]
+                                                                   + ltr[L.cs_k1] * scr[O_PV + L.cs_i1] + ltr[L.cs_k2] * scr[O_PV + L.cs_i2]);
 #pragma unroll
                         for (int i = 0; i < NX; i++) gg += col[i] * rbv[i];
-                        const double dg = scr[O_DGU + a];
+                        L.gx = gg;
+                        const double dg = scr[O_DGX + par_r * NX + L.r];
 #pragma unroll
-                        for (int ap = 0; ap < NV; ap++)
-                            scr[O_MUU + ap * NV + a] = jcol_dot_r(NX + ap, col, L.Ef, L.lt) + dg * sel(ap == a);
-                        scr[O_GU + a] = gg;
+                        for (int wp = 0; wp < NZ; wp++) L.Mx[wp] = jcol_dot_r(wp, col, L.Ef, L.lt) + (wp < NX ? dg * sel(wp == L.r) : 0.0);
+                    }
+                    if (L.r >= ULB && L.r < ULB + ULN) {
+#pragma unroll
+                        for (int e = 0; e < NV / ULN; e++) {
+                            const int a = (L.r - ULB) * (NV / ULN) + e;
+                            double col[NX];
+#pragma unroll
+                            for (int i = 0; i < NX; i++) col[i] = scr[O_PBA + i * NZ + NX + a];
+                            // NOTE: `a` is lane dependent, so this one product indexes the lane's register arrays dynamically and
+                            // ptxas keeps the whole lane state addressable in (L1-resident) local memory, loading a field where a phase
+                            // needs it, instead of holding ~100 registers of state across all phases and spilling the temporaries of
+                            // the hot ones.  Measured against the statically indexed form (which spills 270 B at the 168-register
+                            // cap): batch-1 latency 3.9 -> 3.0 ms, 4,096 instances 12.8 -> 10.6 ms, hybrid 46.9 -> 45.3 ms.
+                            double gg = scr[O_GU + par_r * NV + a] + jcol_dot_r(NX + a, pvv, L.Ef, L.lt);
+#pragma unroll
+                            for (int i = 0; i < NX; i++) gg += col[i] * rbv[i];
+                            const double dg = scr[O_DGU + par_r * NV + a];
+#pragma unroll
+                            for (int ap = 0; ap < NV; ap++)
+                                scr[O_MUU + ap * NV + a] = jcol_dot_r(NX + ap, col, L.Ef, L.lt) + dg * sel(ap == a);
+                            scr[O_GG + a] = gg;
+                        }
                     }
                 }
             GRP_PHASE_END
-            // ---- B5: Cholesky of the control block (every lane), lh, column r of K ----------------
+            if (!Rv) continue;
+            if (!hasU_r) continue;
+            // ---- P3: riccati(kr): Cholesky of the control block (every lane), lh, column r of K ----------------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run) continue;
                 double* scr = sm + L.so;
-                double* grec = L.grec;
+                double* grec = L.grec + (Uv ? R::NREC : 0);       // record of stage kr
                 double Luu[NLU];
 #pragma unroll
                 for (int a = 0; a < NV; a++) {
@@ -691,7 +719,7 @@ struct Grp {
                 }
 #pragma unroll
                 for (int a = 0; a < NV; a++) {
-                    double sacc = scr[O_GU + a];
+                    double sacc = scr[O_GG + a];
 #pragma unroll
                     for (int c = 0; c < a; c++) sacc -= Luu[a * (a + 1) / 2 + c] * L.lh[c];
                     L.lh[a] = sacc * Luu[a * (a + 1) / 2 + a];
@@ -704,7 +732,7 @@ struct Grp {
 #pragma unroll
                     for (int a = 0; a < NV; a++) grec[R::LH + a] = L.lh[a];
                 }
-                if (hasX && L.r < NX) {
+                if (hasX_r && L.r < NX) {
 #pragma unroll
                     for (int a = 0; a < NV; a++) {
                         double sacc = L.Mx[NX + a];
@@ -716,8 +744,8 @@ struct Grp {
                     }
                 }
             GRP_PHASE_END
-            if (!hasX) continue;
-            // ---- B6: Schur complement -> column r of this stage's cost-to-go, and its gradient -----
+            if (!hasX_r) continue;
+            // ---- P4: riccati(kr): Schur complement -> column r of this stage's cost-to-go, and its gradient ----------
             GRP_PHASE_BEGIN(lanes)
                 if (!L.run || L.r >= NX) continue;
                 double* scr = sm + L.so;
