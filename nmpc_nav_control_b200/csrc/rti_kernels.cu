@@ -531,6 +531,8 @@ struct nmpc_solver {
     int hyb_kmax = 12; double hyb_frac = 0.3;   // hand over once fewer than 30 % of the chunk iterate (diff flat 0.3-0.5, tric best <= 0.3)
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
+    // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
+    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false;
     size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
     nmpc_ipm_opts opts;
@@ -815,7 +817,7 @@ static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const d
 {
     using GP = Grp<M, G>;
     const size_t smem = (size_t)GRP_WARPS * GP::WARP_D * sizeof(double);
-    static int blocks_per_sm = 0;          // per template instantiation
+    int& blocks_per_sm = s->grp_blocks_per_sm;
     if (!blocks_per_sm) {
         CK(cudaFuncSetAttribute(k_ipm_group<M, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
@@ -880,7 +882,7 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
             const int nb = (n + LANES * SW_TILES - 1) / (LANES * SW_TILES), nt = LANES * SW_TILES;
             int* act = s->d_cnt;                 // act[it]: lanes entering iteration it
             const size_t smB = (size_t)S::CarryB::SC_N * NMPC_SCRATCH_STRIDE * sizeof(double);
-            static bool attr_set = false;         // per template instantiation (= per model)
+            bool& attr_set = s->sweep_attr_set;
             if (!attr_set) {
                 CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
                 CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
@@ -946,7 +948,7 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
     k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
     s->last_launches++;
     const size_t sm_lin = (size_t)LING_BLOCK * ((GR::LHD + GR::NREC - GR::MC) | 1) * sizeof(double);
-    static bool attr_set = false;
+    bool& attr_set = s->lin_attr_set;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(k_linearize_g<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lin));
         attr_set = true;
