@@ -43,12 +43,13 @@ struct IpmOpts {
 //   IT  : QP iterate (slacks, multipliers, primal, dynamics multipliers)
 //   ST  : steps
 //   FA  : factorisation of the last B sweep
-template <int NV_>
+template <int NV_, int ER_ = 3>
 struct Rec {
+    static constexpr int ER = ER_;             // stored pose rows of [A|B]: the theta row is a per-stage constant for diff / omni4 (Tables::thr)
     static constexpr int NV = NV_, NX = 3 + 2 * NV, NU = NV, NZ = NX + NU, NC = 1 + 3 * NV, NB2 = 2 * NV;
     // ---- LIN
-    static constexpr int E = 0;                 // 3*NC   pose rows of [A|B], columns [theta | actual | ref | u]
-    static constexpr int DLB = E + 3 * NC;      // NB2    lb - z   for [u; ref]
+    static constexpr int E = 0;                 // ER*NC  pose rows of [A|B], columns [theta | actual | ref | u]
+    static constexpr int DLB = E + ER * NC;     // NB2    lb - z   for [u; ref]
     static constexpr int DUB = DLB + NB2;       // NB2    ub - z
     static constexpr int Q = DUB + NB2;         // NZ     QP gradient, order [u; x]
     static constexpr int B0 = Q + NZ;           // NX     b = phi(x,u) - x_next
@@ -86,20 +87,18 @@ struct Rec {
 struct StageIn { const double *lin, *it, *st, *fa; };
 struct StageOut { double *it, *st, *fa; };
 
-template <int NV>
+template <class R>
 NMPC_HD StageOut tile_stage_out(double* tile_lane, int k)
 {
-    using R = Rec<NV>;
     StageOut o;
     o.it = tile_lane + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
     o.st = tile_lane + R::OFF_ST + (size_t)k * R::NF_ST * LANES;
     o.fa = tile_lane + R::OFF_FA + (size_t)k * R::NF_FA * LANES;
     return o;
 }
-template <int NV>
+template <class R>
 NMPC_HD StageIn tile_stage_in(const double* tile_lane, int k)
 {
-    using R = Rec<NV>;
     StageIn i;
     i.lin = tile_lane + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES;
     i.it = tile_lane + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
@@ -119,6 +118,7 @@ struct Tables {
     const double* p;      // [N][NP]
     const double* lti;    // [N][4*NV] av, ar, au, ru per channel (written by the LTI set-up kernel)
     double dt;
+    const double* thr;    // [N][NC] theta row of [A|B] (columns theta | actual | ref | u) where it does not depend on the state (diff, omni4)
     const double* stg;    // [N+1][TROW] group path: per stage av|ar|au|ru, the constants 0 and 1, then the diagonal of W; rows padded to even (Grp::TROW)
 };
 
@@ -135,7 +135,7 @@ struct Rti {
     static constexpr int NC = 1 + 3 * NV, NB2 = 2 * NV, NPK = NX * (NX + 1) / 2, NLU = NV * (NV + 1) / 2;
     static constexpr int NCON = 2 * (NV + (NSTAGE - 1) * NB2 + NV);   // one-sided constraints
     static constexpr int PSTRIDE = NMPC_SCRATCH_STRIDE;               // element stride of the per-lane scratch column
-    using R = Rec<NV>;
+    using R = Rec<NV, M::THETA_ROW_LTI ? 2 : 3>;
     using L = Lin<NV>;
 
     NMPC_HD static constexpr int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
@@ -242,7 +242,7 @@ struct Rti {
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int c = 0; c < NC; c++) lin[(RR::E + i * NC + c) * LS] = Ep[i][c];
+                for (int c = 0; c < NC; c++) if (i < RR::ER) lin[(RR::E + i * NC + c) * LS] = Ep[i][c];
 #pragma unroll
             for (int i = 0; i < NX; i++) lin[(RR::B0 + i) * LS] = xn[i] - xk1[i];
             const double* Wk = tb.W + k * NY;
@@ -326,12 +326,12 @@ struct Rti {
     // ------------------------------------------------------------------------------------
     // structured products with [B A] of one stage
     // ------------------------------------------------------------------------------------
-    NMPC_HD static void load_lin(const double* lin, const double* lti, L& l)
+    NMPC_HD static void load_lin(const double* lin, const double* lti, const double* thr, L& l)
     {
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int c = 0; c < NC; c++) l.E[i][c] = lin[(R::E + i * NC + c) * LANES];
+            for (int c = 0; c < NC; c++) l.E[i][c] = i < R::ER ? lin[(R::E + i * NC + c) * LANES] : thr[c];
 #pragma unroll
         for (int c = 0; c < NV; c++) { l.av[c] = lti[c]; l.ar[c] = lti[NV + c]; l.au[c] = lti[2 * NV + c]; l.ru[c] = lti[3 * NV + c]; }
     }
@@ -503,7 +503,7 @@ struct Rti {
         L lin;
         double v1u[NV], v1x[NX], v2u[NV], v2x[NX];
         if (hasU) {
-            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
             double pio[NX], dpi[NX];
 #pragma unroll
             for (int j = 0; j < NX; j++) { pio[j] = sc[(C::SC_PIO + j) * PSTRIDE]; dpi[j] = sc[(C::SC_DPI + j) * PSTRIDE]; }
@@ -665,7 +665,7 @@ struct Rti {
         double* Pn = sc + (size_t)C::SC_P * PSTRIDE;              // ... overwritten in place by this stage's
         if (hasU) {
             L lin;
-            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
 #pragma unroll
             for (int i = 0; i < NX; i++) out.fa[(R::RB + i) * LANES] = rb[i];
             {
@@ -844,7 +844,7 @@ struct Rti {
         }
         if (hasU) {
             L lin;
-            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
             double xnew[NX];
             apply(lin, du, cy.dx, xnew);
 #pragma unroll
@@ -872,7 +872,7 @@ struct Rti {
         for (int j = 0; j < NX; j++) qx[j] = 0.0;
         if (hasU) {
             L lin;
-            load_lin(in.lin, tb.lti + k * 4 * NV, lin);
+            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
             apply_T(lin, cy.dp, qu, qx);
         }
 #pragma unroll
@@ -996,7 +996,7 @@ struct Rti {
 #pragma unroll 1
         for (int s = 0; s <= NSTAGE; s++) {
             const int k = backward ? NSTAGE - s : s;
-            f(k, tile_stage_in<NV>(tile_lane, k), tile_stage_out<NV>(tile_lane, k));
+            f(k, tile_stage_in<R>(tile_lane, k), tile_stage_out<R>(tile_lane, k));
         }
     }
 

@@ -55,6 +55,7 @@ template <int NV_>
 struct GRec {
     static constexpr int NV = NV_, NX = 3 + 2 * NV, NU = NV, NZ = NX + NU, NC = 1 + 3 * NV, NB2 = 2 * NV,
                          NLU = NV * (NV + 1) / 2;
+    static constexpr int ER = 3;                   // all three pose rows of [A|B] are stored
     static constexpr int ev(int n) { return (n + 1) & ~1; }
     static constexpr int Q = 0;                    // NZ    QP gradient
     static constexpr int B0 = Q + NZ;              // NX    b = phi(x,u) - x_next
@@ -354,16 +355,19 @@ struct Grp {
     // hand-over from the per-sweep path: stage k of one instance from its tile (Rec<NV>, lane-resolved pointer,
     // field stride LANES) into a group record.  State right after a factorising sweep: QP data, iterate,
     // factorisation (the steps DZ / DZA / MC / LHD are rewritten before they are read again).
-    NMPC_HD static void tile_to_record(const double* tl, int k, double* rec)
+    NMPC_HD static void tile_to_record(const double* tl, int k, double* rec, const double* thr_k)
     {
         using T = typename S::R;
         const double* lin = tl + T::OFF_LIN + (size_t)k * T::NF_LIN * LANES;
         const double* it = tl + T::OFF_IT + (size_t)k * T::NF_IT * LANES;
         const double* fa = tl + T::OFF_FA + (size_t)k * T::NF_FA * LANES;
         for (int i = 0; i < NZ; i++) rec[R::Q + i] = lin[(T::Q + i) * LANES];
-        for (int i = 0; i < NX; i++) rec[R::B0 + i] = lin[(T::B0 + i) * LANES];
+        for (int i = 0; i < NX; i++) rec[R::B0 + i] = k < NSTAGE ? lin[(T::B0 + i) * LANES] : 0.0;
         for (int i = 0; i < NB2; i++) { rec[R::DLB + i] = lin[(T::DLB + i) * LANES]; rec[R::DUB + i] = lin[(T::DUB + i) * LANES]; }
-        for (int i = 0; i < 3 * NC; i++) rec[R::E + i] = lin[(T::E + i) * LANES];
+        // the terminal stage has no dynamics: its E is never written in the tile, and the group kernel multiplies it by
+        // zero carries, so it must be finite
+        for (int i = 0; i < T::ER * NC; i++) rec[R::E + i] = k < NSTAGE ? lin[(T::E + i) * LANES] : 0.0;
+        for (int i = T::ER * NC; i < 3 * NC; i++) rec[R::E + i] = k < NSTAGE ? thr_k[i - 2 * NC] : 0.0;   // theta row from the stage table
         for (int i = 0; i < NLU; i++) rec[R::LUU + i] = fa[(T::LUU + i) * LANES];
         for (int i = 0; i < NV * NX; i++) rec[R::KH + i] = fa[(T::KH + i) * LANES];
         for (int i = 0; i < NV; i++) rec[R::LH + i] = fa[(T::LH + i) * LANES];

@@ -40,7 +40,7 @@ static int set_err(int code, const char* what, cudaError_t e = cudaSuccess)
 // kernels
 // ------------------------------------------------------------------------------------------
 template <class M>
-__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti)
+__global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __restrict__ lti, double* __restrict__ thr)
 {
     using S = Rti<M>;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +51,7 @@ __global__ void k_lti_setup(const double* __restrict__ p, double dt, double* __r
     for (int i = 0; i < S::NP; i++) pk[i] = p[k * S::NP + i];
     S::rk4_sens(x0, u0, pk, dt, xn, Ep, out);
     for (int i = 0; i < 4 * S::NV; i++) lti[k * 4 * S::NV + i] = out[i];
+    for (int c = 0; c < S::NC; c++) thr[k * S::NC + c] = Ep[2][c];      // theta row of the sensitivities (state independent for diff / omni4)
 }
 
 // stage table of the group path: row k = [av|ar|au|ru (4 NV), 0, 1, pad | diagonal of W (NY), pad]; row N is zero
@@ -332,7 +333,8 @@ __global__ void k_handover_assign(int nchunk, int ldc, const double* __restrict_
 // (A variant with four field slices per instance and one block per tile was slower: 3.0 ms against 2.0 ms.)
 template <class M, int G>
 __global__ void __launch_bounds__(128)
-k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp)
+k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp,
+                   const double* __restrict__ thr)
 {
     using GP = Grp<M, G>;
     using R = typename Rti<M>::R;
@@ -340,7 +342,8 @@ k_handover_convert(int nchunk, const int* __restrict__ map, const double* __rest
     if (li >= nchunk) return;
     const int q = map[li];
     if (q < 0) return;
-    GP::tile_to_record(ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES), k, GP::rec_of(ws_grp, q, k));
+    GP::tile_to_record(ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES), k, GP::rec_of(ws_grp, q, k),
+                       thr + (size_t)(k < NSTAGE ? k : 0) * Rti<M>::NC);
 }
 // K4 for the hybrid schedule: the step of an instance comes from its tile or, if it was handed over, from its group record
 template <class M>
@@ -540,7 +543,7 @@ struct nmpc_solver {
     std::vector<double> W, We, lbx, ubx, lbu, ubu, p;
     // device
     double *d_tab = nullptr;      // W | We | lbx | ubx | lbu | ubu | p | lti
-    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_stg, tab_doubles;
+    size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_thr, off_stg, tab_doubles;
     int t_w = 0, trow = 0;
     bool tab_dirty = true, p_dirty = true;
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
@@ -584,9 +587,9 @@ extern "C" const char* nmpc_last_error(void) { return g_err; }
 static size_t tile_doubles_of(int model)
 {
     switch (model) {
-        case 0: return Rec<2>::tile_doubles;
-        case 1: return Rec<4>::tile_doubles;
-        default: return Rec<2>::tile_doubles;
+        case 0: return Rti<DiffModel>::R::tile_doubles;
+        case 1: return Rti<Omni4Model>::R::tile_doubles;
+        default: return Rti<TricModel>::R::tile_doubles;
     }
 }
 
@@ -625,6 +628,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     s->off_ubu = off; off += (size_t)n * nv;
     s->off_p = off; off += (size_t)n * m.np;
     s->off_lti = off; off += (size_t)n * 4 * nv;
+    s->off_thr = off; off += (size_t)n * (1 + 3 * nv);
     s->t_w = (4 * nv + 2 + 1) & ~1; s->trow = s->t_w + ((ny + 1) & ~1);
     off = (off + 1) & ~(size_t)1;      // 16-byte aligned rows (cp.async)
     s->off_stg = off; off += (size_t)(n + 1) * s->trow;
@@ -750,7 +754,7 @@ extern "C" int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o)
 template <class M>
 static int launch_lti(nmpc_solver* s, cudaStream_t st)
 {
-    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti);
+    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti, s->d_tab + s->off_thr);
     CK(cudaGetLastError());
     return 0;
 }
@@ -787,7 +791,7 @@ static Tables make_tables(const nmpc_solver* s)
     tb.W = s->d_tab + s->off_W; tb.We = s->d_tab + s->off_We;
     tb.lbx = s->d_tab + s->off_lbx; tb.ubx = s->d_tab + s->off_ubx;
     tb.lbu = s->d_tab + s->off_lbu; tb.ubu = s->d_tab + s->off_ubu;
-    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.stg = s->d_tab + s->off_stg;
+    tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.stg = s->d_tab + s->off_stg; tb.thr = s->d_tab + s->off_thr;
     tb.dt = 1.0 / 40.0;
     return tb;
 }
@@ -911,9 +915,9 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 k_handover_count<<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, s->d_map);
                 k_handover_assign<M><<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, nres, s->d_list, s->d_map, s->d_ctl_g);
                 dim3 gc((n + 127) / 128, NSTAGE + 1);
-                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
-                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
-                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g);
+                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, 128, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
                 const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
                 rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nres, s->d_list, s->d_ctl_g}, st);
                 if (rc) return rc;

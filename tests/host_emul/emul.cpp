@@ -19,12 +19,13 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
     using S = Rti<M>;
     using R = typename S::R;
     constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
-    std::vector<double> lti(NSTAGE * 4 * NV);
+    std::vector<double> lti(NSTAGE * 4 * NV), thr(NSTAGE * S::NC);
     for (int k = 0; k < NSTAGE; k++) {
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+        for (int c = 0; c < S::NC; c++) thr[k * S::NC + c] = Ep[2][c];
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, nullptr};
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, thr.data(), nullptr};
     std::vector<double> tile(R::tile_doubles);
     for (int i = 0; i < B; i++) {
         std::fill(tile.begin(), tile.end(), 0.0);
@@ -73,10 +74,11 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
     using GP = Grp<M, G>;
     using GR = typename GP::R;
     constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
-    std::vector<double> lti(NSTAGE * 4 * NV);
+    std::vector<double> lti(NSTAGE * 4 * NV), thr(NSTAGE * S::NC);
     for (int k = 0; k < NSTAGE; k++) {
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+        for (int c = 0; c < S::NC; c++) thr[k * S::NC + c] = Ep[2][c];
     }
     std::vector<double> stg((NSTAGE + 1) * GP::TROW, 0.0);
     for (int k = 0; k < NSTAGE; k++) {
@@ -84,7 +86,7 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
         stg[k * GP::TROW + GP::LT_ONE] = 1.0;
         for (int i = 0; i < S::NY; i++) stg[k * GP::TROW + GP::T_W + i] = W[k * S::NY + i];
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, stg.data()};
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, thr.data(), stg.data()};
     std::vector<double> ws((size_t)B * GR::inst_doubles, 0.0);
     std::vector<double> WeT;                  // kernel layout of the per-instance terminal weights: [nx][B]
     if (We_inst) { WeT.resize((size_t)NX * B); for (int i = 0; i < B; i++) for (int j = 0; j < NX; j++) WeT[(size_t)j * B + i] = We_inst[(size_t)i * NX + j]; }
@@ -154,10 +156,11 @@ static int run_hybrid(int K, int B, const double* W, const double* We, const dou
     using GP = Grp<M, G>;
     using GR = typename GP::R;
     constexpr int NX = S::NX, NU = S::NU, NV = S::NV;
-    std::vector<double> lti(NSTAGE * 4 * NV);
+    std::vector<double> lti(NSTAGE * 4 * NV), thr(NSTAGE * S::NC);
     for (int k = 0; k < NSTAGE; k++) {
         double x0[NX] = {0}, u0[NU] = {0}, xn[NX], Ep[3][S::NC];
         S::rk4_sens(x0, u0, p + k * S::NP, dt, xn, Ep, &lti[k * 4 * NV]);
+        for (int c = 0; c < S::NC; c++) thr[k * S::NC + c] = Ep[2][c];
     }
     std::vector<double> stg((NSTAGE + 1) * GP::TROW, 0.0);
     for (int k = 0; k < NSTAGE; k++) {
@@ -165,7 +168,7 @@ static int run_hybrid(int K, int B, const double* W, const double* We, const dou
         stg[k * GP::TROW + GP::LT_ONE] = 1.0;
         for (int i = 0; i < S::NY; i++) stg[k * GP::TROW + GP::T_W + i] = W[k * S::NY + i];
     }
-    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, stg.data()};
+    Tables tb{W, We, lbx, ubx, lbu, ubu, p, lti.data(), dt, thr.data(), stg.data()};
     std::vector<std::vector<double>> tiles(B, std::vector<double>(R::tile_doubles, 0.0));
     std::vector<typename S::LaneCtl> ctl(B);
     std::vector<int> qs(B, -1), qi(B, 0), list;
@@ -202,7 +205,7 @@ static int run_hybrid(int K, int B, const double* W, const double* We, const dou
     std::vector<double> ws((size_t)std::max(nres, 1) * GR::inst_doubles, 0.0);
     for (int q = 0; q < nres; q++)
         for (int k = 0; k <= NSTAGE; k++)
-            GP::tile_to_record(tiles[list[q]].data() + (list[q] % LANES), k, GP::rec_of(ws.data(), q, k));
+            GP::tile_to_record(tiles[list[q]].data() + (list[q] % LANES), k, GP::rec_of(ws.data(), q, k), thr.data() + (k < NSTAGE ? k : 0) * S::NC);
     GrpOut out{qs.data(), qi.data(), st.data(), B};
     int next = 0;
     {
