@@ -162,3 +162,42 @@ def test_golden_vectors_two_steps(name):
     assert (out2["qp_iter"] == g["qp_iter2"]).all()
     lr = g["lin_res2"]
     assert parity_report(x2, g["x2"], lr)[0] == 0 and parity_report(u2, g["u2"], lr)[0] == 0
+
+
+def test_error_paths_and_bad_instances(oracle_mod):
+    """argument errors are integer codes (the wrapper turns non-zero into std::runtime_error, NMPCNavControl.cpp:5-23; the
+    library never throws or aborts); a NaN in one instance's measurement fails that instance only (acados status 4 = QP
+    failure, iterate left untouched) and the rest of the batch solves as if it were not there; max-iter is accepted"""
+    import ctypes as C
+    from nmpc_nav_control_b200 import _lib
+    from nmpc_nav_control_b200.solver import BatchedRtiSolver
+    spec = MODELS["diff"]
+    B = 300
+    _, x0, yref, _ = instances("diff", 40, B)
+    s = BatchedRtiSolver(spec, B)
+    lib = s.lib
+    # capacity / argument errors
+    u0 = np.empty((B + 1, spec.nu)); x1 = np.empty((B + 1, spec.nx)); st = np.empty(B + 1, np.int32); it = np.empty(B + 1, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    big = np.zeros((B + 1, spec.nx)); bigy = np.zeros((B + 1, spec.n + 1, spec.ny))
+    assert lib.nmpc_rti_solve_host(s._h, B + 1, p(big), p(bigy), spec.ny, None, p(u0), p(x1), p(st), p(it)) == -4      # NMPC_E_CAPACITY
+    assert lib.nmpc_rti_solve_host(s._h, 0, p(big), p(bigy), spec.ny, None, p(u0), p(x1), p(st), p(it)) == -1          # NMPC_E_ARG
+    assert lib.nmpc_rti_solve_host(s._h, B, p(big), p(bigy), 5, None, p(u0), p(x1), p(st), p(it)) == -1                # nyref must be 3 or ny
+    assert len(lib.nmpc_last_error()) > 0
+    # one poisoned instance
+    ref = oracle_solve(oracle_mod, "diff", x0, yref)
+    xb = x0.copy(); xb[17, 2] = np.nan
+    s.reset()
+    out = s.solve_host(xb, yref)
+    assert out["status"][17] == 4 and (np.delete(out["status"], 17) == 0).all()
+    keep = np.arange(B) != 17
+    assert (out["qp_iter"][keep] == ref["qp_iter"][keep]).all()
+    assert parity_report(out["u0"][keep], ref["u"][keep, 0])[0] == 0
+    x, u = s.get_iterate(B)
+    assert np.abs(x[17, 1:]).max() == 0.0 and np.abs(u[17]).max() == 0.0          # the failed instance's iterate is untouched (reset = zero)
+    # iteration limit: max-iter QPs are accepted (acados SQP_RTI takes the QP max-iter solution), count = limit
+    s.set_opts(iter_max=4)
+    s.reset()
+    out = s.solve_host(x0, yref)
+    assert (out["status"] == 0).all() and out["qp_iter"].max() == 4 and (out["qp_iter"] == np.minimum(ref["qp_iter"], 4)).all()
+    s.close()
