@@ -105,6 +105,36 @@ int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const do
 int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
                         double* u0, double* x1, int* status, int* qp_iter);
 
+/* ---- the controller's per-tick glue, batched and on the device ---------------
+ * One call = NMPCNavControl{Diff,Omni4,Tric}::run for B robots (src/nmpc_nav_control/NMPCNavControlDiff.cpp:82-175,
+ * NMPCNavControlOmni4.cpp:91-177, NMPCNavControlTric.cpp:88-181): initial state from pose + direct kinematics of the
+ * measured twist + the reference states carried from the previous tick, heading references unwrapped along the chain
+ * that starts at the robot's heading, reference list padded with its last pose to N+1 rows, (diff) terminal weights
+ * W_e[0..2] = 100 x W[0..2] when the last two reference rows coincide, one RTI step on the solver's persisted iterate,
+ * reference states advanced by u_0 * dt, inverse kinematics.  The kinematic constant is p[0] of stage 0 (dist_b /
+ * l1_plus_l2), W and W_e are the solver's tables (the wrappers initialise W_e from Q: set it with nmpc_set_weights).
+ *   d_pose [3][B]           x, y, theta
+ *   d_vel  [3][B]           v, vn, w (measured body twist; vn is used by omni4 only)
+ *   d_steer [B] or NULL     tric: measured steering-wheel angle
+ *   d_refs [nref_max][3][B] reference poses x, y, theta (theta wrapped; rows beyond N+1 are ignored)
+ *   d_nref [B] or NULL      number of valid reference poses per robot, clamped to 1..nref_max (NULL = nref_max for all)
+ *   dt                      controller period (1 / control_freq, NMPCNavControlROS.cpp:82)
+ *   d_cmd  [3][B]           out: diff (v, w, 0), omni4 (v, vn, w), tric (v, alpha, 0); a robot whose solve did not
+ *                           return 0 keeps its previous command and carried state (run() throws before writing them)
+ *   d_status, d_qp_iter     [B] or NULL
+ * Asynchronous on `stream`.  nmpc_ctrl_reset zeroes the carried reference states (the constructors' state,
+ * Diff.cpp:14); nmpc_reset is reset_mpc().  nmpc_ctrl_state_device exposes them: [nv][max_batch]. */
+int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                          const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd,
+                          int* d_status, int* d_qp_iter, void* stream);
+int nmpc_ctrl_reset(nmpc_solver* s, void* stream);
+int nmpc_ctrl_state_device(nmpc_solver* s, double** d_vref, int* leading_dim);
+/* host-buffer form: pose [B][3], vel [B][3], steer [B] or NULL, refs [B][nref_max][3] (nref_max <= N+1), nref [B] or
+ * NULL, cmd [B][3] in/out, status [B], qp_iter [B] or NULL.  Synchronous. */
+int nmpc_ctrl_tick_host(nmpc_solver* s, int B, const double* pose, const double* vel, const double* steer,
+                        const double* refs, const int* nref, int nref_max, double dt, double* cmd, int* status,
+                        int* qp_iter);
+
 /* statistics of the last nmpc_rti_solve_host call, stats [8][B] (rows as d_stats above), host pointer */
 int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats);
 

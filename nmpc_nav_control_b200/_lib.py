@@ -17,6 +17,7 @@ SYMBOLS = [
     "nmpc_iterate_device", "nmpc_reset", "nmpc_reset_async", "nmpc_set_iterate_host", "nmpc_get_iterate_host",
     "nmpc_rti_solve_device", "nmpc_rti_solve_host", "nmpc_last_stats_host", "nmpc_last_timing", "nmpc_last_launches",
     "nmpc_dfma_peak_tflops",
+    "nmpc_ctrl_tick_device", "nmpc_ctrl_reset", "nmpc_ctrl_state_device", "nmpc_ctrl_tick_host",
 ]
 
 
@@ -67,6 +68,10 @@ def load() -> C.CDLL:
         lib.nmpc_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
         lib.nmpc_last_launches.argtypes = [vp]
         lib.nmpc_dims.argtypes = [C.c_int, C.POINTER(Dims)]
+        lib.nmpc_ctrl_tick_device.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, dp, ip, ip, vp]
+        lib.nmpc_ctrl_reset.argtypes = [vp, vp]
+        lib.nmpc_ctrl_state_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        lib.nmpc_ctrl_tick_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, dp, ip, ip]
         _lib = lib
     return _lib
 

@@ -19,6 +19,7 @@
 
 #include "rti_core.cuh"
 #include "rti_group.cuh"
+#include "ctrl_glue.cuh"
 #include "../../include/nmpc_b200.h"
 
 using namespace nmpc;
@@ -541,6 +542,30 @@ static const ModelInfo g_models[3] = {
      {-1, -30.0 * DEG}, {1, 30.0 * DEG}, {-1, -120.0 * DEG}, {1, 120.0 * DEG}},
 };
 
+// ---- controller glue around the solve, one thread per instance (ctrl_glue.cuh) ----
+template <class M>
+__global__ void k_ctrl_pre(int B, const double* __restrict__ pose, const double* __restrict__ vel, const double* __restrict__ steer,
+                           const double* __restrict__ refs, const int* __restrict__ nref, int nref_max, const double* __restrict__ vref,
+                           int ldv, const double* __restrict__ p, const double* __restrict__ W0, const double* __restrict__ We_tab,
+                           double* __restrict__ x0bar, double* __restrict__ yref, double* __restrict__ We)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int n = nref ? nref[i] : nref_max;
+    if (n > nref_max) n = nref_max;
+    CtrlGlue<M>::pre(pose + i, vel + i, steer ? steer + i : nullptr, refs + i, n, vref + i, (size_t)ldv, p, W0, We_tab,
+                     x0bar + i, yref + i, We ? We + i : nullptr, (size_t)B);
+}
+template <class M>
+__global__ void k_ctrl_post(int B, const int* __restrict__ status, const double* __restrict__ x0bar, const double* __restrict__ u,
+                            int ldu, double dt, const double* __restrict__ p, double* __restrict__ vref, int ldv,
+                            double* __restrict__ cmd)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    CtrlGlue<M>::post(status[i], x0bar + i, (size_t)B, u + i, (size_t)ldu, dt, p, vref + i, (size_t)ldv, cmd + i);
+}
+
 struct nmpc_solver {
     int model, cap, device, chunk;
     int k3_group = 2;            // K3 schedule: 0 per-sweep kernels (rti_core.cuh), 1 lane-group persistent kernel (rti_group.cuh),
@@ -548,7 +573,7 @@ struct nmpc_solver {
     double *d_ws_g = nullptr;    // group workspace (schedules 1, 2)
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
-    int hyb_kmax = 12; double hyb_frac = 0.3;   // hand over once fewer than 30 % of the chunk iterate (diff flat 0.3-0.5, tric best <= 0.3)
+    int hyb_kmax = 12; double hyb_frac = 0.6;   // hand over once fewer than 60 % of the chunk iterate (sweep in profiles/README_r01_notes.txt)
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
@@ -575,6 +600,8 @@ struct nmpc_solver {
     int *d_status = nullptr, *d_iter = nullptr;
     double *d_stats = nullptr;                   // [8][cap] statistics of the last host call
     int last_host_B = 0;
+    double *d_vref = nullptr;                    // controller glue: carried reference states [nv][cap]
+    double *d_cin = nullptr; int *d_cnref = nullptr;   // controller glue, host call: pose | vel | steer | cmd | refs (SoA, ld = B)
     cudaStream_t own_stream = nullptr;
     std::vector<cudaEvent_t> ev;                 // 4 per chunk + 2
     int n_ev_chunks = 0;
@@ -703,7 +730,7 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
 {
     if (!s) return 0;
     cudaSetDevice(s->device);
-    cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
+    cudaFree(s->d_vref); cudaFree(s->d_cin); cudaFree(s->d_cnref); cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
     cudaFree(s->d_ctl_d); cudaFree(s->d_ctl_i); cudaFree(s->d_cnt);
     cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
@@ -1170,6 +1197,119 @@ extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, c
         CK(cudaMemcpyAsync(qp_iter, s->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     s->last_launches += We ? 5 : 4;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- batched controller tick (declared in include/nmpc_b200.h) ------------------
+static int ensure_ctrl(nmpc_solver* s)
+{
+    if (s->d_vref) return 0;
+    CK(cudaMalloc(&s->d_vref, (size_t)s->cap * s->mi.nv * sizeof(double)));
+    CK(cudaMemset(s->d_vref, 0, (size_t)s->cap * s->mi.nv * sizeof(double)));
+    return 0;
+}
+
+extern "C" int nmpc_ctrl_reset(nmpc_solver* s, void* stream)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_ctrl(s);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s->d_vref, 0, (size_t)s->cap * s->mi.nv * sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int nmpc_ctrl_state_device(nmpc_solver* s, double** d_vref, int* leading_dim)
+{
+    if (!s) return set_err(NMPC_E_ARG, "null solver");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_ctrl(s);
+    if (rc) return rc;
+    if (d_vref) *d_vref = s->d_vref;
+    if (leading_dim) *leading_dim = s->cap;
+    return 0;
+}
+
+extern "C" int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                                     const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd,
+                                     int* d_status, int* d_qp_iter, void* stream)
+{
+    if (!s || !d_pose || !d_vel || !d_refs || !d_cmd) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_ctrl_tick_device: batch exceeds capacity");
+    if (nref_max < 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: nref_max < 1 (run() needs at least one reference pose)");
+    if (s->model == NMPC_MODEL_TRIC && !d_steer) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: tric needs the measured steering angle");
+    if (!(dt > 0.0)) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: dt must be positive");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_staging(s);
+    if (rc) return rc;
+    rc = ensure_ctrl(s);
+    if (rc) return rc;
+    rc = upload_tables(s, st);
+    if (rc) return rc;
+    if (!d_status) d_status = s->d_status;
+    if (!d_qp_iter) d_qp_iter = s->d_iter;
+    const double* p = s->d_tab + s->off_p;
+    const double* W0 = s->d_tab + s->off_W;
+    const double* Wt = s->d_tab + s->off_We;
+    double* We = s->model == NMPC_MODEL_DIFF ? s->d_We : nullptr;      // only the diff wrapper switches W_e (Diff.cpp:126-139)
+    const int nb = (B + 127) / 128;
+    switch (s->model) {
+        case 0: k_ctrl_pre<DiffModel><<<nb, 128, 0, st>>>(B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, s->d_vref, s->cap, p, W0, Wt, s->d_x0bar, s->d_yref, We); break;
+        case 1: k_ctrl_pre<Omni4Model><<<nb, 128, 0, st>>>(B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, s->d_vref, s->cap, p, W0, Wt, s->d_x0bar, s->d_yref, We); break;
+        default: k_ctrl_pre<TricModel><<<nb, 128, 0, st>>>(B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, s->d_vref, s->cap, p, W0, Wt, s->d_x0bar, s->d_yref, We); break;
+    }
+    CK(cudaGetLastError());
+    rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, 3, We, nullptr, nullptr, 0, d_status, d_qp_iter, nullptr, stream);
+    if (rc) return rc;
+    switch (s->model) {
+        case 0: k_ctrl_post<DiffModel><<<nb, 128, 0, st>>>(B, d_status, s->d_x0bar, s->d_u, s->cap, dt, p, s->d_vref, s->cap, d_cmd); break;
+        case 1: k_ctrl_post<Omni4Model><<<nb, 128, 0, st>>>(B, d_status, s->d_x0bar, s->d_u, s->cap, dt, p, s->d_vref, s->cap, d_cmd); break;
+        default: k_ctrl_post<TricModel><<<nb, 128, 0, st>>>(B, d_status, s->d_x0bar, s->d_u, s->cap, dt, p, s->d_vref, s->cap, d_cmd); break;
+    }
+    CK(cudaGetLastError());
+    s->last_launches += 2;
+    return 0;
+}
+
+// host-buffer form of the tick: instance-major arrays, copied and transposed on the device like nmpc_rti_solve_host
+extern "C" int nmpc_ctrl_tick_host(nmpc_solver* s, int B, const double* pose, const double* vel, const double* steer,
+                                   const double* refs, const int* nref, int nref_max, double dt, double* cmd, int* status,
+                                   int* qp_iter)
+{
+    if (!s || !pose || !vel || !refs || !cmd || !status) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_host: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_host: B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_ctrl_tick_host: batch exceeds capacity");
+    if (nref_max < 1 || nref_max > NSTAGE + 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_host: nref_max must be 1..N+1");
+    if (s->model == NMPC_MODEL_TRIC && !steer) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_host: tric needs the measured steering angle");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_staging(s); if (rc) return rc;
+    const size_t cap = s->cap;
+    if (!s->d_cin) {
+        CK(cudaMalloc(&s->d_cin, cap * (10 + 3 * (NSTAGE + 1)) * sizeof(double)));
+        CK(cudaMalloc(&s->d_cnref, cap * sizeof(int)));
+    }
+    cudaStream_t st = s->own_stream;
+    double *d_pose = s->d_cin, *d_vel = d_pose + 3 * cap, *d_steer = d_vel + 3 * cap, *d_cmd = d_steer + cap, *d_refs = d_cmd + 3 * cap;
+    rc = h2d_transpose(s, B, 3, pose, d_pose, B, st); if (rc) return rc;
+    rc = h2d_transpose(s, B, 3, vel, d_vel, B, st); if (rc) return rc;
+    if (steer) CK(cudaMemcpyAsync(d_steer, steer, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = h2d_transpose(s, B, 3 * nref_max, refs, d_refs, B, st); if (rc) return rc;
+    if (nref) CK(cudaMemcpyAsync(s->d_cnref, nref, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the command of an instance whose solve fails is left as the caller passed it (run() throws before writing it)
+    rc = h2d_transpose(s, B, 3, cmd, d_cmd, B, st); if (rc) return rc;
+    rc = nmpc_ctrl_tick_device(s, B, d_pose, d_vel, steer ? d_steer : nullptr, d_refs, nref ? s->d_cnref : nullptr, nref_max, dt,
+                               d_cmd, s->d_status, s->d_iter, st);
+    if (rc) return rc;
+    dim3 b(32, 8), g((B + 31) / 32, 1);
+    k_soa_to_aos<<<g, b, 0, st>>>(B, 3, B, d_cmd, s->d_out_aos);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cmd, s->d_out_aos, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, s->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (qp_iter) CK(cudaMemcpyAsync(qp_iter, s->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    s->last_launches += 5;
     CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -65,3 +65,36 @@ def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, gr
                       status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), _dp(stats))
     assert rc >= 0
     return dict(x=x, u=u, qp_status=status, qp_iter=iters, stats=stats, resumed=rc)
+
+
+def emul_ctrl_pre(name, pose, vel, steer, refs, nref, vref, tables):
+    """controller glue before the solve (ctrl_glue.cuh CtrlGlue::pre) on SoA arrays: pose [3,B], vel [3,B], steer [B] or
+    None, refs [nref_max,3,B], nref [B] or None, vref [nv,B]; returns x0bar [nx,B], yref [N+1,3,B], We [nx,B] (diff) or None"""
+    lib = build()
+    spec = MODELS[name]
+    B = pose.shape[1]
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pose, vel, refs, vref = c(pose), c(vel), c(refs), c(vref)
+    steer = None if steer is None else c(steer)
+    nref_a = None if nref is None else np.ascontiguousarray(nref, dtype=np.int32)
+    x0bar = np.zeros((spec.nx, B)); yref = np.zeros((spec.n + 1, 3, B))
+    We = np.zeros((spec.nx, B)) if name == "diff" else None
+    p, W0, Wt = c(tables["p"][0]), c(tables["W"][0]), c(tables["We"])
+    lib.emul_ctrl_pre(C.c_int(spec.model_id), C.c_int(B), _dp(pose), _dp(vel), None if steer is None else _dp(steer), _dp(refs),
+                      None if nref_a is None else nref_a.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(refs.shape[0]), _dp(vref),
+                      _dp(p), _dp(W0), _dp(Wt), _dp(x0bar), _dp(yref), None if We is None else _dp(We))
+    return x0bar, yref, We
+
+
+def emul_ctrl_post(name, status, x0bar, u0, dt, vref, cmd, tables):
+    """controller glue after the solve (CtrlGlue::post): status [B], x0bar [nx,B], u0 [nu,B]; updates and returns vref [nv,B],
+    cmd [3,B] (instances with a non-zero status keep both)"""
+    lib = build()
+    spec = MODELS[name]
+    B = x0bar.shape[1]
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    st = np.ascontiguousarray(status, dtype=np.int32)
+    vref, cmd = c(vref).copy(), c(cmd).copy()
+    lib.emul_ctrl_post(C.c_int(spec.model_id), C.c_int(B), st.ctypes.data_as(C.POINTER(C.c_int)), _dp(c(x0bar)), _dp(c(u0)),
+                       C.c_double(dt), _dp(c(tables["p"][0])), _dp(vref), _dp(cmd))
+    return vref, cmd

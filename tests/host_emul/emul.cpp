@@ -243,3 +243,48 @@ extern "C" int emul_rti_hybrid(int model, int K, int B, const double* W, const d
 #undef RH
     return -1;
 }
+
+// ---- controller glue (ctrl_glue.cuh), one instance after another; arrays SoA with leading dimension B ----
+#include "../../nmpc_nav_control_b200/csrc/ctrl_glue.cuh"
+
+template <class M>
+static void ctrl_pre_all(int B, const double* pose, const double* vel, const double* steer, const double* refs, const int* nref,
+                         int nref_max, const double* vref, const double* p, const double* W0, const double* We_tab,
+                         double* x0bar, double* yref, double* We)
+{
+    for (int i = 0; i < B; i++) {
+        int n = nref ? nref[i] : nref_max;
+        if (n > nref_max) n = nref_max;
+        CtrlGlue<M>::pre(pose + i, vel + i, steer ? steer + i : nullptr, refs + i, n, vref + i, (size_t)B, p, W0, We_tab,
+                         x0bar + i, yref + i, We ? We + i : nullptr, (size_t)B);
+    }
+}
+template <class M>
+static void ctrl_post_all(int B, const int* status, const double* x0bar, const double* u0, double dt, const double* p,
+                          double* vref, double* cmd)
+{
+    for (int i = 0; i < B; i++)
+        CtrlGlue<M>::post(status[i], x0bar + i, (size_t)B, u0 + i, (size_t)B, dt, p, vref + i, (size_t)B, cmd + i);
+}
+
+extern "C" int emul_ctrl_pre(int model, int B, const double* pose, const double* vel, const double* steer, const double* refs,
+                             const int* nref, int nref_max, const double* vref, const double* p, const double* W0,
+                             const double* We_tab, double* x0bar, double* yref, double* We)
+{
+    switch (model) {
+        case 0: ctrl_pre_all<DiffModel>(B, pose, vel, steer, refs, nref, nref_max, vref, p, W0, We_tab, x0bar, yref, We); break;
+        case 1: ctrl_pre_all<Omni4Model>(B, pose, vel, steer, refs, nref, nref_max, vref, p, W0, We_tab, x0bar, yref, We); break;
+        default: ctrl_pre_all<TricModel>(B, pose, vel, steer, refs, nref, nref_max, vref, p, W0, We_tab, x0bar, yref, We); break;
+    }
+    return 0;
+}
+extern "C" int emul_ctrl_post(int model, int B, const int* status, const double* x0bar, const double* u0, double dt,
+                              const double* p, double* vref, double* cmd)
+{
+    switch (model) {
+        case 0: ctrl_post_all<DiffModel>(B, status, x0bar, u0, dt, p, vref, cmd); break;
+        case 1: ctrl_post_all<Omni4Model>(B, status, x0bar, u0, dt, p, vref, cmd); break;
+        default: ctrl_post_all<TricModel>(B, status, x0bar, u0, dt, p, vref, cmd); break;
+    }
+    return 0;
+}

@@ -108,5 +108,5 @@ if __name__ == "__main__":
             continue
         n, b = item.split(":")
         print(json.dumps(throughput(n, int(b))), flush=True)
-    for n in ("diff", "omni4", "tric"):
+    for n in ("diff", "omni4", "tric") if a.latency_calls > 0 else ():
         print(json.dumps(latency(n, a.latency_calls)), flush=True)
