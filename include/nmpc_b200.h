@@ -135,6 +135,31 @@ int nmpc_ctrl_tick_host(nmpc_solver* s, int B, const double* pose, const double*
                         const double* refs, const int* nref, int nref_max, double dt, double* cmd, int* status,
                         int* qp_iter);
 
+/* ---- batched path discretisation ----------------------------------------------
+ * PathDiscretizer::getNextNPoses (src/nmpc_nav_control/PathDiscretizer.cpp:14-63) for B robots: from the robot's
+ * nearest path parameter, walk the path in steps of a tenth of the distance covered in one sample period at the
+ * segment's speed, emit a pose each time the accumulated chord length reaches that distance (within 1 %), pad with the
+ * path's end pose.  The reference's curves are `parametric_trajectories_common::TPath`, a private dependency; here a
+ * path is a run of segments, sixteen doubles each: */
+typedef struct {
+    double kind;        /* 0: x(u) = sum cx[i] u^i, y(u) = sum cy[i] u^i (line, cubic Bezier, up to degree 5)            */
+                        /* 1: arc x(u) = cx[0] + cx[1] cos(cx[2] + cx[3] u), y(u) = cy[0] + cx[1] sin(cx[2] + cx[3] u)    */
+    double vel;         /* signed speed on the segment (TPath::GetVelocity); negative = heading flipped by pi            */
+    double th0, th1;    /* holonomic heading at u = 0 and u = 1 (TPath::GetThetaHolomonic, linear in between)            */
+    double cx[6], cy[6];
+} nmpc_path_segment;
+/*   d_segments [n_seg][16]     all paths' segments, path q = segments d_path_offsets[q] .. d_path_offsets[q+1]-1
+ *   d_path_offsets [n_paths+1] (int)
+ *   d_path_id [B] (int) or NULL (= path 0 for every robot), clamped to 0..n_paths-1
+ *   d_nearest_u [B]            segment index + parameter in [0,1) (active_path_u_, NMPCNavControlROS.cpp:668)
+ *   sample_period, num_poses, is_holonomic   the constructor arguments (PathDiscretizer.cpp:5-12; the node passes
+ *                              dt, N+1, false: NMPCNavControlROS.cpp:666)
+ *   d_poses [num_poses][3][B]  out: x, y, theta - the d_refs layout of nmpc_ctrl_tick_device
+ * Stateless; asynchronous on `stream` of device `device`. */
+int nmpc_path_discretize_device(int device, int B, const double* d_segments, const int* d_path_offsets, int n_paths,
+                                const int* d_path_id, const double* d_nearest_u, double sample_period, int num_poses,
+                                int is_holonomic, double* d_poses, void* stream);
+
 /* statistics of the last nmpc_rti_solve_host call, stats [8][B] (rows as d_stats above), host pointer */
 int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats);
 

@@ -20,6 +20,7 @@
 #include "rti_core.cuh"
 #include "rti_group.cuh"
 #include "ctrl_glue.cuh"
+#include "path_disc.cuh"
 #include "../../include/nmpc_b200.h"
 
 using namespace nmpc;
@@ -541,6 +542,19 @@ static const ModelInfo g_models[3] = {
     {7, 2, 3, 2, {0.270, 0.1, 0.5}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
      {-1, -30.0 * DEG}, {1, 30.0 * DEG}, {-1, -120.0 * DEG}, {1, 120.0 * DEG}},
 };
+
+// ---- batched path discretisation, one thread per robot (path_disc.cuh) ----------
+__global__ void k_path_discretize(int B, const double* __restrict__ segs, const int* __restrict__ path_off, int n_paths,
+                                  const int* __restrict__ path_id, const double* __restrict__ u0, double period, int num_poses,
+                                  int holonomic, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int p = path_id ? path_id[i] : 0;
+    p = p < 0 ? 0 : (p >= n_paths ? n_paths - 1 : p);
+    const int s0 = path_off[p], s1 = path_off[p + 1];
+    PathDisc::next_poses(segs + (size_t)s0 * PathDisc::SEG, s1 - s0, u0[i], period, num_poses, holonomic != 0, out + i, (size_t)B);
+}
 
 // ---- controller glue around the solve, one thread per instance (ctrl_glue.cuh) ----
 template <class M>
@@ -1311,6 +1325,24 @@ extern "C" int nmpc_ctrl_tick_host(nmpc_solver* s, int B, const double* pose, co
     if (qp_iter) CK(cudaMemcpyAsync(qp_iter, s->d_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
     s->last_launches += 5;
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- batched path discretisation (declared in include/nmpc_b200.h) --------------
+extern "C" int nmpc_path_discretize_device(int device, int B, const double* d_segments, const int* d_path_offsets, int n_paths,
+                                           const int* d_path_id, const double* d_nearest_u, double sample_period, int num_poses,
+                                           int is_holonomic, double* d_poses, void* stream)
+{
+    if (!d_segments || !d_path_offsets || !d_nearest_u || !d_poses) return set_err(NMPC_E_ARG, "nmpc_path_discretize_device: null argument");
+    if (B < 1 || n_paths < 1 || num_poses < 1) return set_err(NMPC_E_ARG, "nmpc_path_discretize_device: B, n_paths and num_poses must be >= 1");
+    if (!(sample_period > 0.0)) return set_err(NMPC_E_ARG, "nmpc_path_discretize_device: sample_period must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return set_err(NMPC_E_NODEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(NMPC_E_ARG, "nmpc_path_discretize_device: bad device");
+    CK(cudaSetDevice(device));
+    k_path_discretize<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(B, d_segments, d_path_offsets, n_paths, d_path_id, d_nearest_u,
+                                                                     sample_period, num_poses, is_holonomic, d_poses);
+    CK(cudaGetLastError());
     return 0;
 }
 

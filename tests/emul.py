@@ -98,3 +98,16 @@ def emul_ctrl_post(name, status, x0bar, u0, dt, vref, cmd, tables):
     lib.emul_ctrl_post(C.c_int(spec.model_id), C.c_int(B), st.ctypes.data_as(C.POINTER(C.c_int)), _dp(c(x0bar)), _dp(c(u0)),
                        C.c_double(dt), _dp(c(tables["p"][0])), _dp(vref), _dp(cmd))
     return vref, cmd
+
+
+def emul_path_discretize(segments, offsets, path_id, u0, period, num_poses, holonomic=False):
+    """path discretisation (path_disc.cuh PathDisc::next_poses): returns poses [num_poses, 3, B]"""
+    lib = build()
+    seg = np.ascontiguousarray(segments, dtype=np.float64); off = np.ascontiguousarray(offsets, dtype=np.int32)
+    pid = np.ascontiguousarray(path_id, dtype=np.int32); u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    B = len(u0)
+    out = np.zeros((num_poses, 3, B))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    lib.emul_path_discretize(C.c_int(B), _dp(seg), ip(off), C.c_int(len(off) - 1), ip(pid), _dp(u0), C.c_double(period),
+                             C.c_int(num_poses), C.c_int(int(holonomic)), _dp(out))
+    return out

@@ -288,3 +288,17 @@ extern "C" int emul_ctrl_post(int model, int B, const int* status, const double*
     }
     return 0;
 }
+
+// ---- path discretisation (path_disc.cuh), one robot after another; poses SoA [num_poses][3][B] ----
+#include "../../nmpc_nav_control_b200/csrc/path_disc.cuh"
+extern "C" int emul_path_discretize(int B, const double* segs, const int* path_off, int n_paths, const int* path_id, const double* u0,
+                                    double period, int num_poses, int holonomic, double* out)
+{
+    for (int i = 0; i < B; i++) {
+        int p = path_id ? path_id[i] : 0;
+        p = p < 0 ? 0 : (p >= n_paths ? n_paths - 1 : p);
+        PathDisc::next_poses(segs + (size_t)path_off[p] * PathDisc::SEG, path_off[p + 1] - path_off[p], u0[i], period, num_poses,
+                             holonomic != 0, out + i, (size_t)B);
+    }
+    return 0;
+}

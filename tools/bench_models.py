@@ -59,6 +59,66 @@ def latency(name, calls):
     return r
 
 
+def ctrl_tick(name, B, steps=3, warm=2):
+    """the batched controller tick (glue kernels + RTI step) on device-resident inputs, cold iterate
+    every step like the bench line, and the same through the host-buffer call"""
+    from nmpc_nav_control_b200.controller import BatchedNavController
+    spec = MODELS[name]
+    dev = torch.device("cuda", 0)
+    inst = synth.make_instances(spec, 0, B, device=dev, pose_only=True)
+    yref = inst["yref"].permute(1, 2, 0).contiguous()                 # [N+1, 3, B]: the reference poses
+    pose = inst["x0"].t().contiguous()[:3].contiguous()
+    # the bench workload seen from the controller's side: measured twist = inverse kinematics of the actuator states
+    # (exact for diff and tric, least-squares for omni4's four wheels), carried reference states = x0[3+nv:]
+    a = inst["x0"].t().contiguous()[3:3 + spec.nv]
+    vref0 = inst["x0"].t().contiguous()[3 + spec.nv:].contiguous()
+    vel = torch.zeros(3, B, dtype=torch.float64, device=dev)
+    steer = None
+    if name == "diff":
+        vel[0] = (a[1] + a[0]) / 2.0; vel[2] = (a[1] - a[0]) / spec.p[0]
+    elif name == "omni4":
+        vel[0] = (a[0] - a[1] + a[2] - a[3]) / 4.0; vel[1] = (-a[0] - a[1] + a[2] + a[3]) / 4.0
+        vel[2] = (-a[0] - a[1] - a[2] - a[3]) / (2.0 * spec.p[0])
+    else:
+        vel[0] = a[0]; steer = a[1].contiguous()
+    th = yref[:, 2, :]
+    refs = yref.clone(); refs[:, 2, :] = torch.atan2(torch.sin(th), torch.cos(th))      # wrapped, as a path planner gives them
+    c = BatchedNavController(spec, B, dt=spec.dt)
+    if steer is not None:
+        c.set_steering_wheel_angle(steer)
+    carried = c.reference_states()[:, :B]
+    out = None
+
+    def step():
+        nonlocal out
+        c.solver.reset_async(); carried.copy_(vref0)
+        out = c.run(pose, vel, refs, out=out)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t = c.solver.last_timing()
+    hp, hv, hr = pose.t().contiguous().cpu().numpy(), vel.t().contiguous().cpu().numpy(), refs.permute(2, 0, 1).contiguous().cpu().numpy()
+    ho = None
+    hs = []
+    for _ in range(warm + steps):
+        c.solver.reset(); carried.copy_(vref0); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ho = c.run_host(hp, hv, hr, out=ho)
+        hs.append((time.perf_counter() - t0) * 1e3)
+    r = dict(kind="controller_tick", model=name, batch=B, ms_per_tick=ms, ticks_per_s=B / ms * 1e3, solver_ms=t,
+             glue_ms=ms - t["total_ms"], host_ms_per_tick=float(np.mean(hs[warm:])), host_ticks_per_s=B / float(np.mean(hs[warm:])) * 1e3,
+             status_nonzero=int((out["status"] != 0).sum()), mean_qp_iter=float(out["qp_iter"].double().mean()),
+             h2d_bytes_per_tick=int(hp.nbytes + hv.nbytes + hr.nbytes + ho["cmd"].nbytes), d2h_bytes_per_tick=int(ho["cmd"].nbytes + 8 * B))
+    c.close()
+    return r
+
+
 def mixed(total, steps=2, warm=1):
     """BASELINE config 5 on one GPU: `total` instances split in thirds over omni4 / diff / tric, one solver and one
     CUDA stream per model so that the three launch sequences overlap; device-resident inputs"""
@@ -99,7 +159,13 @@ if __name__ == "__main__":
     ap.add_argument("--latency-calls", type=int, default=1000)
     ap.add_argument("--batches", default="diff:65536,diff:131072,tric:65536,omni4:65536,omni4:262144")
     ap.add_argument("--mixed", type=int, default=0, help="BASELINE config 5: total instances of the mixed omni4/diff/tric batch")
+    ap.add_argument("--ctrl", default="", help="SURVEY 8(f1): controller tick, e.g. diff:65536,tric:65536")
     a = ap.parse_args()
+    if a.ctrl:
+        for item in a.ctrl.split(","):
+            n, b = item.split(":")
+            print(json.dumps(ctrl_tick(n, int(b))), flush=True)
+        sys.exit(0)
     if a.mixed:
         print(json.dumps(mixed(a.mixed)), flush=True)
         sys.exit(0)
