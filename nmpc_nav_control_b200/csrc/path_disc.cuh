@@ -34,10 +34,9 @@ struct PathDisc {
         else if (fl < 0.0) { num = 0; u = 0.0; }
         return segs + (size_t)num * SEG;
     }
-    NMPC_HD static void sample(const double* segs, int nseg, double su, bool hol, double& x, double& y, double& th, double& dx,
-                               double& dy)
+    // position and tangent at path parameter su; returns the segment and its local parameter for heading()
+    NMPC_HD static const double* sample(const double* segs, int nseg, double su, double& u, double& x, double& y, double& dx, double& dy)
     {
-        double u;
         const double* s = locate(segs, nseg, su, u);
         if (s[0] == 0.0) {
             x = poly(s + 4, u); y = poly(s + 10, u); dx = dpoly(s + 4, u); dy = dpoly(s + 10, u);
@@ -46,8 +45,16 @@ struct PathDisc {
             nmpc_sincos(s[6] + s[7] * u, &sn, &cs);
             x = s[4] + s[5] * cs; y = s[10] + s[5] * sn; dx = -s[5] * s[7] * sn; dy = s[5] * s[7] * cs;
         }
-        if (hol) th = s[2] + (s[3] - s[2]) * u;                     // GetThetaHolomonic
-        else { th = atan2(dy, dx); if (!(s[1] >= 0.0)) th += PI; }   // :80-83
+        return s;
+    }
+    // the heading getPoseSample returns (:78-84); only evaluated for the poses that are emitted - upstream computes it
+    // at every sub-step and throws nine of ten away
+    NMPC_HD static double heading(const double* s, double u, double dx, double dy, bool hol)
+    {
+        if (hol) return s[2] + (s[3] - s[2]) * u;                   // GetThetaHolomonic
+        double th = atan2(dy, dx);
+        if (!(s[1] >= 0.0)) th += PI;
+        return th;
     }
     NMPC_HD static double seg_speed(const double* segs, int nseg, double fl)
     {
@@ -63,8 +70,8 @@ struct PathDisc {
         const double thr = 1e-2, N = (double)nseg;
         double goal = seg_speed(segs, nseg, floor(u0)) * period;
         double rel = goal / per_cycle;
-        double u = u0, ox, oy, th, dx, dy;
-        sample(segs, nseg, u0, hol, ox, oy, th, dx, dy);
+        double u = u0, ox, oy, dx, dy, ul;
+        sample(segs, nseg, u0, ul, ox, oy, dx, dy);
         double step = rel / sqrt(dx * dx + dy * dy);
         double curr = 0.0;
         int n = 0;
@@ -72,11 +79,12 @@ struct PathDisc {
             u += step;
             u = (N < u) ? N : u;                                    // std::min(u, N): a NaN stays and ends the walk
             double nx, ny;
-            sample(segs, nseg, u, hol, nx, ny, th, dx, dy);
+            const double* sg = sample(segs, nseg, u, ul, nx, ny, dx, dy);
             const double ex = nx - ox, ey = ny - oy;
             curr += sqrt(ex * ex + ey * ey);
             if ((goal - curr) <= thr * goal) {
-                out[(size_t)(3 * n) * ld] = nx; out[(size_t)(3 * n + 1) * ld] = ny; out[(size_t)(3 * n + 2) * ld] = th;
+                out[(size_t)(3 * n) * ld] = nx; out[(size_t)(3 * n + 1) * ld] = ny;
+                out[(size_t)(3 * n + 2) * ld] = heading(sg, ul, dx, dy, hol);
                 n++;
                 const double fl = floor(u);
                 goal = seg_speed(segs, nseg, fl < N - 1.0 ? fl : N - 1.0) * period;
@@ -88,8 +96,9 @@ struct PathDisc {
             ox = nx; oy = ny;
         }
         if (n < num_poses) {                                        // :58-63
-            double lx, ly, lt;
-            sample(segs, nseg, N, hol, lx, ly, lt, dx, dy);
+            double lx, ly;
+            const double* sg = sample(segs, nseg, N, ul, lx, ly, dx, dy);
+            const double lt = heading(sg, ul, dx, dy, hol);
             for (; n < num_poses; n++) {
                 out[(size_t)(3 * n) * ld] = lx; out[(size_t)(3 * n + 1) * ld] = ly; out[(size_t)(3 * n + 2) * ld] = lt;
             }

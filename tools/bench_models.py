@@ -119,6 +119,31 @@ def ctrl_tick(name, B, steps=3, warm=2):
     return r
 
 
+def pathdisc(B, steps=20, warm=3):
+    """N+1 reference poses for B robots on 512 seeded paths (lines, arcs, cubic Beziers)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pathcases
+    from nmpc_nav_control_b200 import paths as P
+    paths, pid, _ = pathcases.cases(seed=9, n_paths=512, B=B)
+    rng = np.random.default_rng(1)
+    u0 = rng.uniform(0, 1, B) * np.array([len(paths[p]) for p in pid])
+    ps = P.PathSet(paths)
+    d = P.BatchedPathDiscretizer(0.025, 81, False)
+    tp, tu = torch.from_numpy(pid).cuda(), torch.from_numpy(u0).cuda()
+    out = d.get_next_n_poses(ps, tp, tu)
+    for _ in range(warm):
+        d.get_next_n_poses(ps, tp, tu, out=out)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        d.get_next_n_poses(ps, tp, tu, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(kind="path_discretise", robots=B, poses=81, ms_per_call=ms, robots_per_s=B / ms * 1e3,
+                out_bytes=int(out.numel() * 8), out_GBps=out.numel() * 8 / ms / 1e6)
+
+
 def mixed(total, steps=2, warm=1):
     """BASELINE config 5 on one GPU: `total` instances split in thirds over omni4 / diff / tric, one solver and one
     CUDA stream per model so that the three launch sequences overlap; device-resident inputs"""
@@ -160,7 +185,11 @@ if __name__ == "__main__":
     ap.add_argument("--batches", default="diff:65536,diff:131072,tric:65536,omni4:65536,omni4:262144")
     ap.add_argument("--mixed", type=int, default=0, help="BASELINE config 5: total instances of the mixed omni4/diff/tric batch")
     ap.add_argument("--ctrl", default="", help="SURVEY 8(f1): controller tick, e.g. diff:65536,tric:65536")
+    ap.add_argument("--paths", type=int, default=0, help="SURVEY 8(f2): path discretisation for this many robots")
     a = ap.parse_args()
+    if a.paths:
+        print(json.dumps(pathdisc(a.paths)), flush=True)
+        sys.exit(0)
     if a.ctrl:
         for item in a.ctrl.split(","):
             n, b = item.split(":")
