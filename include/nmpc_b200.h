@@ -160,6 +160,23 @@ int nmpc_path_discretize_device(int device, int B, const double* d_segments, con
                                 const int* d_path_id, const double* d_nearest_u, double sample_period, int num_poses,
                                 int is_holonomic, double* d_poses, void* stream);
 
+/* ---- the remaining pieces of a closed loop on the device --------------------------
+ * nmpc_plant_step_device: the nominal plant of a rollout, x+ = phi_RK4(x, u_0 + noise) over `dt` with the solver's own
+ * model and parameters (stage 0), u_0 = stage-0 controls of the solver's persisted iterate (what the tick just
+ * computed); scripts/test_scripts/acados_sim_diff.py:136-160 is the reference's version (Euler, Gaussian noise on the
+ * accelerations).  Writes the measurements the next tick reads.
+ *   d_noise [nu][B] or NULL    added to u_0 (the caller draws it; seeded)
+ *   d_xplant [nx][B]           plant state, in/out
+ *   d_pose [3][B], d_vel [3][B] (v, vn, w: inverse kinematics of the actuator states), d_steer [B] or NULL (tric)
+ * nmpc_path_nearest_device: path parameter nearest to each robot's position, searched in
+ * [u - back, u + ahead] (clipped to the path) by 24 coarse samples and a ternary refinement.  The reference uses the
+ * private parametric_trajectories_common::TPathProcessMinDist (NMPCNavControlROS.cpp:596-600); this is a stand-in
+ * with its own definition.   d_u [B]: in = previous parameter, out = nearest. */
+int nmpc_plant_step_device(nmpc_solver* s, int B, double dt, const double* d_noise, double* d_xplant, double* d_pose,
+                           double* d_vel, double* d_steer, void* stream);
+int nmpc_path_nearest_device(int device, int B, const double* d_segments, const int* d_path_offsets, int n_paths,
+                             const int* d_path_id, const double* d_pose, double back, double ahead, double* d_u, void* stream);
+
 /* statistics of the last nmpc_rti_solve_host call, stats [8][B] (rows as d_stats above), host pointer */
 int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats);
 

@@ -18,7 +18,7 @@ SYMBOLS = [
     "nmpc_rti_solve_device", "nmpc_rti_solve_host", "nmpc_last_stats_host", "nmpc_last_timing", "nmpc_last_launches",
     "nmpc_dfma_peak_tflops",
     "nmpc_ctrl_tick_device", "nmpc_ctrl_reset", "nmpc_ctrl_state_device", "nmpc_ctrl_tick_host",
-    "nmpc_path_discretize_device",
+    "nmpc_path_discretize_device", "nmpc_plant_step_device", "nmpc_path_nearest_device",
 ]
 
 
@@ -71,6 +71,8 @@ def load() -> C.CDLL:
         lib.nmpc_dims.argtypes = [C.c_int, C.POINTER(Dims)]
         lib.nmpc_ctrl_tick_device.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, dp, ip, ip, vp]
         lib.nmpc_path_discretize_device.argtypes = [C.c_int, C.c_int, dp, ip, C.c_int, ip, dp, C.c_double, C.c_int, C.c_int, dp, vp]
+        lib.nmpc_plant_step_device.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, dp, vp]
+        lib.nmpc_path_nearest_device.argtypes = [C.c_int, C.c_int, dp, ip, C.c_int, ip, dp, C.c_double, C.c_double, dp, vp]
         lib.nmpc_ctrl_reset.argtypes = [vp, vp]
         lib.nmpc_ctrl_state_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
         lib.nmpc_ctrl_tick_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, dp, ip, ip]

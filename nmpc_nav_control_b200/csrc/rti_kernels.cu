@@ -21,6 +21,7 @@
 #include "rti_group.cuh"
 #include "ctrl_glue.cuh"
 #include "path_disc.cuh"
+#include "rollout.cuh"
 #include "../../include/nmpc_b200.h"
 
 using namespace nmpc;
@@ -542,6 +543,29 @@ static const ModelInfo g_models[3] = {
     {7, 2, 3, 2, {0.270, 0.1, 0.5}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
      {-1, -30.0 * DEG}, {1, 30.0 * DEG}, {-1, -120.0 * DEG}, {1, 120.0 * DEG}},
 };
+
+// ---- plant step and nearest path parameter, one thread per robot (rollout.cuh) ---
+template <class M>
+__global__ void k_plant_step(int B, double* __restrict__ xp, const double* __restrict__ u, int ldu, const double* __restrict__ noise,
+                             const double* __restrict__ p, double dt, double* __restrict__ pose, double* __restrict__ vel,
+                             double* __restrict__ steer)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Rollout<M>::plant_step(xp + i, (size_t)B, u + i, (size_t)ldu, noise ? noise + i : nullptr, p, dt, pose + i, vel + i,
+                           steer ? steer + i : nullptr);
+}
+__global__ void k_path_nearest(int B, const double* __restrict__ segs, const int* __restrict__ path_off, int n_paths,
+                               const int* __restrict__ path_id, const double* __restrict__ pose, double back, double ahead,
+                               double* __restrict__ u)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int p = path_id ? path_id[i] : 0;
+    p = p < 0 ? 0 : (p >= n_paths ? n_paths - 1 : p);
+    const int s0 = path_off[p], s1 = path_off[p + 1];
+    u[i] = PathNearest::nearest_u(segs + (size_t)s0 * PathDisc::SEG, s1 - s0, u[i], pose[i], pose[(size_t)B + i], back, ahead);
+}
 
 // ---- batched path discretisation, one thread per robot (path_disc.cuh) ----------
 __global__ void k_path_discretize(int B, const double* __restrict__ segs, const int* __restrict__ path_off, int n_paths,
@@ -1342,6 +1366,45 @@ extern "C" int nmpc_path_discretize_device(int device, int B, const double* d_se
     CK(cudaSetDevice(device));
     k_path_discretize<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(B, d_segments, d_path_offsets, n_paths, d_path_id, d_nearest_u,
                                                                      sample_period, num_poses, is_holonomic, d_poses);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- closed-loop pieces (declared in include/nmpc_b200.h) ------------------------
+extern "C" int nmpc_plant_step_device(nmpc_solver* s, int B, double dt, const double* d_noise, double* d_xplant, double* d_pose,
+                                      double* d_vel, double* d_steer, void* stream)
+{
+    if (!s || !d_xplant || !d_pose || !d_vel) return set_err(NMPC_E_ARG, "nmpc_plant_step_device: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_plant_step_device: B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_plant_step_device: batch exceeds capacity");
+    if (!(dt > 0.0)) return set_err(NMPC_E_ARG, "nmpc_plant_step_device: dt must be positive");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_tables(s, st);
+    if (rc) return rc;
+    const double* p = s->d_tab + s->off_p;
+    const int nb = (B + 127) / 128;
+    switch (s->model) {
+        case 0: k_plant_step<DiffModel><<<nb, 128, 0, st>>>(B, d_xplant, s->d_u, s->cap, d_noise, p, dt, d_pose, d_vel, d_steer); break;
+        case 1: k_plant_step<Omni4Model><<<nb, 128, 0, st>>>(B, d_xplant, s->d_u, s->cap, d_noise, p, dt, d_pose, d_vel, d_steer); break;
+        default: k_plant_step<TricModel><<<nb, 128, 0, st>>>(B, d_xplant, s->d_u, s->cap, d_noise, p, dt, d_pose, d_vel, d_steer); break;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nmpc_path_nearest_device(int device, int B, const double* d_segments, const int* d_path_offsets, int n_paths,
+                                        const int* d_path_id, const double* d_pose, double back, double ahead, double* d_u,
+                                        void* stream)
+{
+    if (!d_segments || !d_path_offsets || !d_pose || !d_u) return set_err(NMPC_E_ARG, "nmpc_path_nearest_device: null argument");
+    if (B < 1 || n_paths < 1) return set_err(NMPC_E_ARG, "nmpc_path_nearest_device: B and n_paths must be >= 1");
+    if (!(back >= 0.0) || !(ahead >= 0.0)) return set_err(NMPC_E_ARG, "nmpc_path_nearest_device: the search window must be non-negative");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return set_err(NMPC_E_NODEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(NMPC_E_ARG, "nmpc_path_nearest_device: bad device");
+    CK(cudaSetDevice(device));
+    k_path_nearest<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(B, d_segments, d_path_offsets, n_paths, d_path_id, d_pose, back, ahead, d_u);
     CK(cudaGetLastError());
     return 0;
 }

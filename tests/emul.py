@@ -111,3 +111,24 @@ def emul_path_discretize(segments, offsets, path_id, u0, period, num_poses, holo
     lib.emul_path_discretize(C.c_int(B), _dp(seg), ip(off), C.c_int(len(off) - 1), ip(pid), _dp(u0), C.c_double(period),
                              C.c_int(num_poses), C.c_int(int(holonomic)), _dp(out))
     return out
+
+
+def emul_plant_step(name, x, u0, noise, p, dt):
+    """plant step (rollout.cuh Rollout::plant_step) on SoA arrays x [nx,B], u0 [nu,B], noise [nu,B] or None;
+    returns x+ [nx,B], pose [3,B], vel [3,B], steer [B]"""
+    lib = build()
+    spec = MODELS[name]
+    B = x.shape[1]
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    xp = c(x).copy(); pose = np.zeros((3, B)); vel = np.zeros((3, B)); steer = np.zeros(B)
+    lib.emul_plant_step(C.c_int(spec.model_id), C.c_int(B), _dp(xp), _dp(c(u0)), None if noise is None else _dp(c(noise)),
+                        _dp(c(p)), C.c_double(dt), _dp(pose), _dp(vel), _dp(steer))
+    return xp, pose, vel, steer
+
+
+def emul_nearest_u(segments, u_prev, px, py, back, ahead):
+    lib = build()
+    lib.emul_nearest_u.restype = C.c_double
+    seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 16)
+    return lib.emul_nearest_u(_dp(seg), C.c_int(len(seg)), C.c_double(u_prev), C.c_double(px), C.c_double(py), C.c_double(back),
+                              C.c_double(ahead))

@@ -302,3 +302,23 @@ extern "C" int emul_path_discretize(int B, const double* segs, const int* path_o
     }
     return 0;
 }
+
+// ---- closed-loop pieces (rollout.cuh) ----
+#include "../../nmpc_nav_control_b200/csrc/rollout.cuh"
+extern "C" int emul_plant_step(int model, int B, double* xp, const double* u0, const double* noise, const double* p, double dt,
+                               double* pose, double* vel, double* steer)
+{
+    for (int i = 0; i < B; i++) {
+        const double* nz = noise ? noise + i : nullptr;
+        switch (model) {
+            case 0: Rollout<DiffModel>::plant_step(xp + i, B, u0 + i, B, nz, p, dt, pose + i, vel + i, steer + i); break;
+            case 1: Rollout<Omni4Model>::plant_step(xp + i, B, u0 + i, B, nz, p, dt, pose + i, vel + i, steer + i); break;
+            default: Rollout<TricModel>::plant_step(xp + i, B, u0 + i, B, nz, p, dt, pose + i, vel + i, steer + i); break;
+        }
+    }
+    return 0;
+}
+extern "C" double emul_nearest_u(const double* segs, int nseg, double u_prev, double px, double py, double back, double ahead)
+{
+    return PathNearest::nearest_u(segs, nseg, u_prev, px, py, back, ahead);
+}
