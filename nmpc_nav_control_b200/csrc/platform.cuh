@@ -27,6 +27,9 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 // per-lane scratch columns live in shared memory on the device, interleaved over the threads of a
 // sweep CTA (bank-conflict free); the host emulation uses a plain array
 #if defined(__CUDACC__)
+#ifndef NMPC_FDF_MINB
+#define NMPC_FDF_MINB 16                // resident single-warp CTAs per SM the solve-sweep kernel is compiled for (16: 128 registers)
+#endif
 #ifndef NMPC_SW_TILES
 #define NMPC_SW_TILES 1                 // tiles (warps) per CTA of a sweep kernel (1: the omni4 factorising sweep fits more warps per SM)
 #endif
