@@ -533,15 +533,10 @@ struct ModelInfo {
     int nx, nu, np, nv;
     double p[3], Q[11], Rw[4], QN[11], lbx[4], ubx[4], lbu[4], ubu[4];
 };
-static const double DEG = 3.14159265358979323846 / 180.0;
-// config/nmpc_nav_control_acados_models.yaml:2-75 through scripts/<m>/generate_c_code.py:30-60
+// config/nmpc_nav_control_acados_models.yaml:2-75 through scripts/<m>/generate_c_code.py:30-60; the table is generated by
+// `python -m nmpc_nav_control_b200.emit <yaml>`, the committed copy is the reference's YAML
 static const ModelInfo g_models[3] = {
-    {7, 2, 2, 2, {0.270, 0.1, 0}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
-     {-1, -1}, {1, 1}, {-2, -2}, {2, 2}},
-    {11, 4, 2, 4, {0.535, 0.1, 0}, {10, 10, 10, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 1, 1}, {10, 10, 10, 0, 0, 0, 0, 0, 0, 0, 0},
-     {-1, -1, -1, -1}, {1, 1, 1, 1}, {-1, -1, -1, -1}, {1, 1, 1, 1}},
-    {7, 2, 3, 2, {0.270, 0.1, 0.5}, {10, 10, 5, 0, 0, 0, 0}, {1, 1}, {1000, 1000, 500, 0, 0, 0, 0},
-     {-1, -30.0 * DEG}, {1, 30.0 * DEG}, {-1, -120.0 * DEG}, {1, 120.0 * DEG}},
+#include "model_defaults.inc"
 };
 
 // ---- plant step and nearest path parameter, one thread per robot (rollout.cuh) ---
