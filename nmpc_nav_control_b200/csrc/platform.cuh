@@ -30,6 +30,9 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #ifndef NMPC_FDF_MINB
 #define NMPC_FDF_MINB 16                // resident single-warp CTAs per SM the solve-sweep kernel is compiled for (16: 128 registers)
 #endif
+#ifndef NMPC_FDF_PREFETCH
+#define NMPC_FDF_PREFETCH 0             // 1: the solve sweeps prefetch the next stage's fields into L2 (rti_core.cuh sweep_lane)
+#endif
 #ifndef NMPC_SW_TILES
 #define NMPC_SW_TILES 1                 // tiles (warps) per CTA of a sweep kernel (1: the omni4 factorising sweep fits more warps per SM)
 #endif
