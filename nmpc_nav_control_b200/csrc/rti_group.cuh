@@ -357,32 +357,57 @@ struct Grp {
     // factorisation (the steps DZ / DZA / MC / LHD are rewritten before they are read again).
     NMPC_HD static void tile_to_record(const double* tl, int k, double* rec, const double* thr_k)
     {
+        tile_to_record_range<0, R::NREC>(tl, k, rec, thr_k);
+    }
+    // entries [D0, D1) of the record into out[0, D1 - D0): the hand-over kernel converts a record in pieces so that its
+    // shared-memory staging stays small (every loop is unrolled, the range tests fold at compile time)
+    template <int D0, int D1>
+    NMPC_HD static void tile_to_record_range(const double* tl, int k, double* out, const double* thr_k)
+    {
         using T = typename S::R;
         const double* lin = tl + T::OFF_LIN + (size_t)k * T::NF_LIN * LANES;
         const double* it = tl + T::OFF_IT + (size_t)k * T::NF_IT * LANES;
         const double* fa = tl + T::OFF_FA + (size_t)k * T::NF_FA * LANES;
-        for (int i = 0; i < NZ; i++) rec[R::Q + i] = lin[(T::Q + i) * LANES];
-        for (int i = 0; i < NX; i++) rec[R::B0 + i] = k < NSTAGE ? lin[(T::B0 + i) * LANES] : 0.0;
-        for (int i = 0; i < NB2; i++) { rec[R::DLB + i] = lin[(T::DLB + i) * LANES]; rec[R::DUB + i] = lin[(T::DUB + i) * LANES]; }
+        const bool dyn = k < NSTAGE;
+#define NMPC_PUT(off, val) do { if ((off) >= D0 && (off) < D1) out[(off) - D0] = (val); } while (0)
+#pragma unroll
+        for (int i = 0; i < NZ; i++) NMPC_PUT(R::Q + i, lin[(T::Q + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < NX; i++) NMPC_PUT(R::B0 + i, dyn ? lin[(T::B0 + i) * LANES] : 0.0);
+#pragma unroll
+        for (int i = 0; i < NB2; i++) { NMPC_PUT(R::DLB + i, lin[(T::DLB + i) * LANES]); NMPC_PUT(R::DUB + i, lin[(T::DUB + i) * LANES]); }
         // the terminal stage has no dynamics: its E is never written in the tile, and the group kernel multiplies it by
         // zero carries, so it must be finite
-        for (int i = 0; i < T::ER * NC; i++) rec[R::E + i] = k < NSTAGE ? lin[(T::E + i) * LANES] : 0.0;
-        for (int i = T::ER * NC; i < 3 * NC; i++) rec[R::E + i] = k < NSTAGE ? thr_k[i - 2 * NC] : 0.0;   // theta row from the stage table
-        for (int i = 0; i < NLU; i++) rec[R::LUU + i] = fa[(T::LUU + i) * LANES];
-        for (int i = 0; i < NV * NX; i++) rec[R::KH + i] = fa[(T::KH + i) * LANES];
-        for (int i = 0; i < NV; i++) rec[R::LH + i] = fa[(T::LH + i) * LANES];
-        for (int i = 0; i < NX; i++) rec[R::RB + i] = fa[(T::RB + i) * LANES];
-        for (int i = 0; i < 2 * NB2; i++) { rec[R::T + i] = it[(T::T + i) * LANES]; rec[R::LAM + i] = it[(T::LAM + i) * LANES]; }
-        for (int i = 0; i < NZ; i++) rec[R::Z + i] = it[(T::Z + i) * LANES];
-        for (int i = 0; i < NX; i++) rec[R::PI + i] = it[(T::PI + i) * LANES];
+#pragma unroll
+        for (int i = 0; i < T::ER * NC; i++) NMPC_PUT(R::E + i, dyn ? lin[(T::E + i) * LANES] : 0.0);
+#pragma unroll
+        for (int i = T::ER * NC; i < 3 * NC; i++) NMPC_PUT(R::E + i, dyn ? thr_k[i - 2 * NC] : 0.0);   // theta row from the stage table
+#pragma unroll
+        for (int i = 0; i < NLU; i++) NMPC_PUT(R::LUU + i, fa[(T::LUU + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < NV * NX; i++) NMPC_PUT(R::KH + i, fa[(T::KH + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < NV; i++) NMPC_PUT(R::LH + i, fa[(T::LH + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < NX; i++) NMPC_PUT(R::RB + i, fa[(T::RB + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < 2 * NB2; i++) { NMPC_PUT(R::T + i, it[(T::T + i) * LANES]); NMPC_PUT(R::LAM + i, it[(T::LAM + i) * LANES]); }
+#pragma unroll
+        for (int i = 0; i < NZ; i++) NMPC_PUT(R::Z + i, it[(T::Z + i) * LANES]);
+#pragma unroll
+        for (int i = 0; i < NX; i++) NMPC_PUT(R::PI + i, it[(T::PI + i) * LANES]);
         // padding and the step fields stay defined (the steps are rewritten before they are read)
-        if ((3 * NC) & 1) rec[R::E + 3 * NC] = 0.0;
-        if (NLU & 1) rec[R::LUU + NLU] = 0.0;
-        if (NX & 1) { rec[R::RB + NX] = 0.0; rec[R::PI + NX] = 0.0; }
-        if (NZ & 1) { rec[R::Z + NZ] = 0.0; rec[R::DZ + NZ] = 0.0; rec[R::DZA + NZ] = 0.0; }
-        for (int i = 0; i < NV; i++) rec[R::LHD + i] = 0.0;
-        for (int i = 0; i < NZ; i++) { rec[R::DZ + i] = 0.0; rec[R::DZA + i] = 0.0; }
-        for (int i = 0; i < 2 * NB2; i++) rec[R::MC + i] = 0.0;
+        if ((3 * NC) & 1) NMPC_PUT(R::E + 3 * NC, 0.0);
+        if (NLU & 1) NMPC_PUT(R::LUU + NLU, 0.0);
+        if (NX & 1) { NMPC_PUT(R::RB + NX, 0.0); NMPC_PUT(R::PI + NX, 0.0); }
+        if (NZ & 1) { NMPC_PUT(R::Z + NZ, 0.0); NMPC_PUT(R::DZ + NZ, 0.0); NMPC_PUT(R::DZA + NZ, 0.0); }
+#pragma unroll
+        for (int i = 0; i < NV; i++) NMPC_PUT(R::LHD + i, 0.0);
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { NMPC_PUT(R::DZ + i, 0.0); NMPC_PUT(R::DZA + i, 0.0); }
+#pragma unroll
+        for (int i = 0; i < 2 * NB2; i++) NMPC_PUT(R::MC + i, 0.0);
+#undef NMPC_PUT
     }
 
     NMPC_HD static double* rec_of(double* ws, int li, int k) { return ws + (size_t)li * R::inst_doubles + (size_t)k * R::NREC; }

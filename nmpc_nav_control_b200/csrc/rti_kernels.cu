@@ -334,12 +334,13 @@ __global__ void k_handover_assign(int nchunk, int ldc, const double* __restrict_
 }
 // state of the unfinished instances from the tile layout into their group records; grid (instances / CV_BLOCK, stages).
 // A thread gathers its instance's fields (coalesced over the lanes of a tile) into a shared-memory row, the block then
-// writes every row out as one contiguous record.  Measured on the diff headline batch (ncu, 65,536 instances, 26 %
+// writes the rows out coalesced, a quarter of the record at a time (19 KB of shared memory per block instead of 71 KB:
+// four times the resident threads).  Measured on the diff headline batch (ncu, 65,536 instances, 26 %
 // handed over): a thread storing its record 8 bytes at a time 2.77 ms; staged through shared memory (this) 2.46 ms;
 // staged, but a thread per UNFINISHED instance in list order (all threads busy, tile reads scattered) 3.17 ms; four
 // field slices per instance with one block per tile 3.0 ms.  The kernel reads 4.3 GB - nearly the whole tile workspace,
 // since a 32-byte sector holds four lanes and 26 % of the lanes are wanted.
-constexpr int CV_BLOCK = 64;
+constexpr int CV_BLOCK = 64, CV_PIECES = 4;
 template <class M, int G>
 __global__ void __launch_bounds__(CV_BLOCK)
 k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp,
@@ -348,22 +349,30 @@ k_handover_convert(int nchunk, const int* __restrict__ map, const double* __rest
     using GP = Grp<M, G>;
     using R = typename Rti<M>::R;
     using GR = typename GP::R;
-    constexpr int ROW = GR::NREC | 1;                 // odd row stride: conflict-free
-    extern __shared__ double cv_sm[];
+    constexpr int PW = ((GR::NREC + CV_PIECES - 1) / CV_PIECES + 1) & ~1;     // piece width, even
+    constexpr int ROW = PW | 1;                                              // odd row stride: conflict-free
+    __shared__ double cv_sm[CV_BLOCK * ROW];
     __shared__ int cv_q[CV_BLOCK];
     const int li = blockIdx.x * CV_BLOCK + threadIdx.x, k = blockIdx.y;
     int q = -1;
     if (li < nchunk) q = map[li];
     cv_q[threadIdx.x] = q;
-    if (q >= 0)
-        GP::tile_to_record(ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES), k, cv_sm + (size_t)threadIdx.x * ROW,
-                           thr + (size_t)(k < NSTAGE ? k : 0) * Rti<M>::NC);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < CV_BLOCK * GR::NREC; idx += CV_BLOCK) {
-        const int r = idx / GR::NREC, d = idx - r * GR::NREC;
-        const int qr = cv_q[r];
-        if (qr >= 0) GP::rec_of(ws_grp, qr, k)[d] = cv_sm[(size_t)r * ROW + d];
-    }
+    const double* tl = ws_tile + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
+    const double* thr_k = thr + (size_t)(k < NSTAGE ? k : 0) * Rti<M>::NC;
+    auto piece = [&](auto pc) {
+        constexpr int D0 = decltype(pc)::value * PW, D1 = D0 + PW < GR::NREC ? D0 + PW : GR::NREC, W = D1 - D0;
+        if (q >= 0) GP::template tile_to_record_range<D0, D1>(tl, k, cv_sm + threadIdx.x * ROW, thr_k);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < CV_BLOCK * W; idx += CV_BLOCK) {
+            const int r = idx / W, d = idx - r * W;
+            const int qr = cv_q[r];
+            if (qr >= 0) GP::rec_of(ws_grp, qr, k)[D0 + d] = cv_sm[r * ROW + d];
+        }
+        __syncthreads();
+    };
+    static_assert(CV_PIECES == 4, "one call per piece below");
+    piece(std::integral_constant<int, 0>{}); piece(std::integral_constant<int, 1>{});
+    piece(std::integral_constant<int, 2>{}); piece(std::integral_constant<int, 3>{});
 }
 // K4 for the hybrid schedule: the step of an instance comes from its tile or, if it was handed over, from its group record
 template <class M>
@@ -992,16 +1001,9 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 k_handover_count<<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, s->d_map);
                 k_handover_assign<M><<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, nres, s->d_list, s->d_map, s->d_ctl_g);
                 dim3 gc((n + CV_BLOCK - 1) / CV_BLOCK, NSTAGE + 1);
-                const size_t smcv = (size_t)CV_BLOCK * (GRec<S::NV>::NREC | 1) * sizeof(double);
-                if (!s->cv_attr_set) {
-                    if (s->grp_G == 16) CK(cudaFuncSetAttribute(k_handover_convert<M, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smcv));
-                    else if (s->grp_G == 32) CK(cudaFuncSetAttribute(k_handover_convert<M, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smcv));
-                    else if constexpr (S::NV == 2) CK(cudaFuncSetAttribute(k_handover_convert<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smcv));
-                    s->cv_attr_set = true;
-                }
-                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, CV_BLOCK, smcv, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
-                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, CV_BLOCK, smcv, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
-                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, CV_BLOCK, smcv, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
                 const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
                 rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nres, s->d_list, s->d_ctl_g}, st);
                 if (rc) return rc;

@@ -63,3 +63,20 @@ def test_no_cpu_fallback():
     assert cap
     assert shim.diff2amr_acados_create(C.c_void_p(cap)) != 0
     shim.diff2amr_acados_free_capsule(C.c_void_p(cap))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_for_the_stateless_entry_points():
+    """the path discretiser and the nearest-parameter search refuse to run without a device, and the
+    host mirrors raise instead of computing anything on the CPU"""
+    import numpy as np
+    from nmpc_nav_control_b200 import _lib
+    lib = _lib.load()
+    a = np.zeros(64); ai = np.zeros(4, dtype=np.int32)
+    p, pi = C.c_void_p(a.ctypes.data), C.c_void_p(ai.ctypes.data)
+    assert lib.nmpc_path_discretize_device(0, 1, p, pi, 1, pi, p, 0.025, 4, 0, p, None) == -3
+    assert b"no CPU fallback" in lib.nmpc_last_error()
+    assert lib.nmpc_path_nearest_device(0, 1, p, pi, 1, pi, p, 0.05, 0.5, p, None) == -3
+    from nmpc_nav_control_b200.controller import BatchedNavController
+    with pytest.raises(RuntimeError):
+        BatchedNavController("diff", 4, dt=0.025)
