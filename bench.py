@@ -136,7 +136,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_per_step": sample, "model": MODEL},
+        "config": {"workload": WORKLOAD, "sample_per_step": sample, "robot_model": MODEL},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": f"{sample} diff instances per step (same generator/seed as the GPU arm), OpenMP one solve per core"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -293,7 +293,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": MODEL, "batch_per_gpu": B, "N": spec.n, "iterate": "reset (zero) before every step",
+        "config": {"workload": WORKLOAD, "robot_model": MODEL, "batch_per_gpu": B, "N": spec.n, "iterate": "reset (zero) before every step",
                    "l2": "inputs (131 MB) and the K3 workspace (5.6 GB tile state streamed by every sweep, 3 GB of group records) "
                          "exceed the 126 MB L2 many times over; no explicit flush",
                    "k3_schedule": os.environ.get("NMPC_K3", "hybrid"),
