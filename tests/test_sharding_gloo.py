@@ -70,3 +70,46 @@ def test_shard_range_and_mixed_split():
             assert max(sizes) - min(sizes) <= 1
     m = mixed_split(1048576)          # 349,526 / 349,525 / 349,525
     assert m == {"omni4": 349526, "diff": 349525, "tric": 349525}
+
+
+def _worker_paths(rank, world, port, total, tmp):
+    """SURVEY 8(f2) under sharding: each rank discretises the paths of its contiguous block of robots (the device code
+    compiled for the host) - robots are independent, the shards need no exchange"""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emul
+    import pathcases
+    from nmpc_nav_control_b200.shard import shard_range
+    paths, pid, u0 = pathcases.cases(seed=17, n_paths=9, B=total)           # every rank derives the same fleet from the seed
+    off = np.cumsum([0] + [len(p) for p in paths]).astype(np.int32)
+    a, b = shard_range(total, rank, world)
+    out = emul.emul_path_discretize(np.concatenate(paths), off, pid[a:b], u0[a:b], 0.025, 81)
+    n = torch.tensor([float(b - a)], dtype=torch.float64)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    assert n.item() == total
+    np.save(os.path.join(tmp, f"poses{rank}.npy"), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_path_discretiser_shards_equal_single_process(tmp_path):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emul
+    import pathcases
+    emul.build()                                       # build once here, not concurrently in the workers
+    total, world = 77, 2
+    ctx = mp.get_context("spawn")
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_paths, args=(r, world, port, total, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    paths, pid, u0 = pathcases.cases(seed=17, n_paths=9, B=total)
+    off = np.cumsum([0] + [len(p) for p in paths]).astype(np.int32)
+    full = emul.emul_path_discretize(np.concatenate(paths), off, pid, u0, 0.025, 81)
+    got = np.concatenate([np.load(os.path.join(tmp_path, f"poses{r}.npy")) for r in range(world)], axis=2)
+    assert np.array_equal(got, full)
