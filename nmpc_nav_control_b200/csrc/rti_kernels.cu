@@ -619,7 +619,7 @@ struct nmpc_solver {
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
-    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false, cv_attr_set = false;
+    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false;
     size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
     nmpc_ipm_opts opts;
