@@ -144,18 +144,19 @@ def pathdisc(B, steps=20, warm=3):
                 out_bytes=int(out.numel() * 8), out_GBps=out.numel() * 8 / ms / 1e6)
 
 
-def mixed(total, steps=2, warm=1):
+def mixed(total, steps=2, warm=1, device=0, start=0, sync=None):
     """BASELINE config 5 on one GPU: `total` instances split in thirds over omni4 / diff / tric, one solver and one
-    CUDA stream per model so that the three launch sequences overlap; device-resident inputs"""
-    dev = torch.device("cuda", 0)
+    CUDA stream per model so that the three launch sequences overlap; device-resident inputs.  `start`: first instance
+    index of this GPU's shard (multi-GPU run), `sync`: barrier called before and after the timed region"""
+    dev = torch.device("cuda", device)
     third = total // 3
     sizes = {"omni4": total - 2 * third, "diff": third, "tric": third}
     ctx = {}
     for name, B in sizes.items():
         spec = MODELS[name]
-        inst = synth.make_instances(spec, 0, B, device=dev, pose_only=True)
+        inst = synth.make_instances(spec, start, B, device=dev, pose_only=True)
         ctx[name] = dict(B=B, x0=inst["x0"].t().contiguous(), yref=inst["yref"].permute(1, 2, 0).contiguous(),
-                         s=BatchedRtiSolver(spec, B), st=torch.cuda.Stream(dev),
+                         s=BatchedRtiSolver(spec, B, device=device), st=torch.cuda.Stream(dev),
                          out=dict(status=torch.empty(B, dtype=torch.int32, device=dev), qp_iter=torch.empty(B, dtype=torch.int32, device=dev)))
     torch.cuda.synchronize()
 
@@ -165,11 +166,15 @@ def mixed(total, steps=2, warm=1):
             c["s"].solve_device(c["x0"], c["yref"], out=c["out"], stream=c["st"])
     for _ in range(warm):
         step()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
+    if sync:
+        sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
+    if sync:
+        sync()
     ms = (time.perf_counter() - t0) * 1e3 / steps
     r = dict(kind="mixed", total=total, sizes=sizes, ms_per_step=ms, solves_per_s=total / ms * 1e3,
              status_nonzero={n: int((c["out"]["status"] != 0).sum()) for n, c in ctx.items()},
