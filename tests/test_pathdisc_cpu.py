@@ -84,3 +84,25 @@ def test_spacing_property():
         vmax = np.abs(paths[pid[i]][:, 1]).max(); vmin = np.abs(paths[pid[i]][:, 1]).min()
         moving = d > 0
         assert (d[moving] <= 1.11 * vmax * 0.025 + 1e-12).all() and (d[moving][:-1] >= 0.85 * vmin * 0.025).all(), i
+
+
+def test_restatement_and_device_code_against_compiled_reference_random_search():
+    """hypothesis-driven search over path shapes, start parameters, sample periods and pose counts: the restatement is
+    bit-identical to the reference's compiled discretiser, the device code (host build) agrees within 1e-12"""
+    if not pathdisc.build_ref():
+        pytest.skip("oracle/_ref/libpathdisc_ref.so not built (needs the reference tree)")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 10**6), nseg=st.integers(1, 6), frac=st.floats(0.0, 0.999), period=st.sampled_from([0.02, 0.025, 0.1, 1.0, 2.5]),
+           num=st.integers(1, 90), hol=st.booleans())
+    def check(seed, nseg, frac, period, num, hol):
+        rng = np.random.default_rng(seed)
+        path = pathcases.random_path(rng, nseg)
+        u0 = frac * nseg
+        want = pathdisc.ref(path, u0, period, num, hol)
+        got = pathdisc.get_next_n_poses(path, u0, period, num, hol)
+        assert np.array_equal(got, want)
+        dev = emul.emul_path_discretize(path, [0, nseg], [0], [u0], period, num, hol)[:, :, 0]
+        assert np.abs(dev - want).max() <= 1e-12
+    check()

@@ -58,3 +58,48 @@ def test_nearest_u_matches_restatement_and_is_a_local_minimum():
     ln = paths[0]
     assert emul.emul_nearest_u(ln, float(len(ln)), 0.0, 0.0, 0.0, 0.0) == float(len(ln))
     assert emul.emul_nearest_u(ln, -5.0, 0.0, 0.0, 0.0, 1.0) == 0.0
+
+
+@pytest.mark.parametrize("name", ["diff", "tric"])
+def test_whole_tick_chain_on_the_host_matches_oracle_chain(oracle_mod, name):
+    """every device function of one closed-loop tick, compiled for the host and chained exactly as
+    nmpc_nav_control_b200/rollout.py chains the kernels (nearest parameter -> path discretiser -> controller glue ->
+    RTI step -> glue -> plant step), against oracle/rollout.py, free running for a few ticks"""
+    spec = MODELS[name]
+    B, T = 6, 4
+    paths, pid, u0 = pathcases.cases(seed=41, n_paths=3, B=B)
+    for p in paths:
+        p[:, 1] = np.clip(np.abs(p[:, 1]), 0.2, 0.6)
+    u0 = np.minimum(u0, np.array([len(paths[p]) for p in pid]) - 0.5)
+    off = np.cumsum([0] + [len(p) for p in paths]).astype(np.int32)
+    segs = np.concatenate(paths)
+    rng = np.random.default_rng(6)
+    start = np.array([pathdisc._pose([pathdisc.Seg(r) for r in paths[p]], u, False) for p, u in zip(pid, u0)])
+    pose0 = start + rng.uniform(-0.03, 0.03, (B, 3))
+    noise = 0.05 * rng.standard_normal((T, spec.nu, B))
+    ctl = orollout.OracleController(None, name)                 # for its tables only (W_e = Q, as the wrappers set it)
+    tb = ctl.tb
+    # device-side state, SoA
+    x_plant = np.zeros((spec.nx, B)); x_plant[:3] = pose0.T
+    pose = pose0.T.copy(); vel = np.zeros((3, B)); steer = np.zeros(B); u = u0.copy()
+    vref = np.zeros((spec.nv, B)); cmd = np.zeros((3, B))
+    xs = np.zeros((B, spec.n + 1, spec.nx)); us = np.zeros((B, spec.n, spec.nu))          # after reset_mpc()
+    oracles = [orollout.OracleRollout(oracle_mod, name, paths[pid[i]], pose0[i], u0[i]) for i in range(B)]
+    for t in range(T):
+        for i in range(B):
+            a, b = off[pid[i]], off[pid[i] + 1]
+            u[i] = emul.emul_nearest_u(segs[a:b], u[i], pose[0, i], pose[1, i], 0.05, 0.5)
+        refs = emul.emul_path_discretize(segs, off, pid, u, spec.dt, spec.n + 1)
+        x0bar, yref, We = emul.emul_ctrl_pre(name, pose, vel, steer if name == "tric" else None, refs, None, vref, tb)
+        r = emul.emul_rti(name, np.ascontiguousarray(x0bar.T), np.ascontiguousarray(np.moveaxis(yref, -1, 0)), xs, us,
+                          We=None if We is None else np.ascontiguousarray(We.T), tables=tb)
+        assert (r["qp_status"] == 0).all()
+        xs, us = r["x"], r["u"]
+        u_first = np.ascontiguousarray(us[:, 0, :].T)
+        vref, cmd = emul.emul_ctrl_post(name, np.zeros(B, np.int32), x0bar, u_first, spec.dt, vref, cmd, tb)
+        x_plant, pose, vel, steer = emul.emul_plant_step(name, x_plant, u_first, noise[t], np.array(spec.p), spec.dt)
+        for i in range(B):
+            want, qi = oracles[i].step(noise[t, :, i])
+            assert r["qp_iter"][i] == qi, (t, i)
+            assert np.abs(cmd[:, i] - np.array(want)).max() <= 1e-9, (t, i, cmd[:, i], want)
+            assert np.abs(pose[:, i] - oracles[i].pose).max() <= 1e-9, (t, i)
