@@ -80,3 +80,19 @@ def test_no_cpu_fallback_for_the_stateless_entry_points():
     from nmpc_nav_control_b200.controller import BatchedNavController
     with pytest.raises(RuntimeError):
         BatchedNavController("diff", 4, dt=0.025)
+
+
+def test_cpp_example_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/fleet_tick.cpp: a plain C++14 caller of include/nmpc_b200.h builds against the library; without a CUDA
+    device it reports the library's error and exits 2 (no CPU fallback)"""
+    from nmpc_nav_control_b200 import build
+    build.build_core()
+    exe = str(tmp_path / "fleet_tick")
+    pkg = os.path.join(ROOT, "nmpc_nav_control_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "fleet_tick.cpp"), "-L", pkg, "-lnmpc_b200", f"-Wl,-rpath,{pkg}", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe, "8"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 2 and "no CPU fallback" in p.stderr, (p.returncode, p.stderr)
