@@ -33,6 +33,23 @@ WORKLOAD = "diff model batched SQP-RTI, 65,536 random initial states/reference p
 MODEL = "diff"
 BATCH = 65536
 # algorithmic bytes and dense-equivalent flops per RTI solve
+N_STAGES = 80
+
+
+def bench_config(batch: int) -> dict:
+    """the workload description, identical for both arms (`--impl ours` / `--impl reference`)"""
+    return {"workload": WORKLOAD, "robot_model": MODEL, "batch_per_gpu": batch, "N": N_STAGES,
+            "iterate": "reset (zero) before every step"}
+
+
+def host_cores() -> int:
+    """cores this process may run on (torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arm sets its own count)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 ALG_BYTES = {"diff": 17512, "tric": 17512, "omni4": 29160}
 F_LIN = {"diff": 3.73e5, "tric": 3.73e5, "omni4": 1.37e6}
 F_ITER = {"diff": 2.69e5, "tric": 2.69e5, "omni4": 8.76e5}
@@ -94,6 +111,7 @@ class ClockSampler:
 
 
 def cpu_baseline(model: str, sample: int, nthreads: int = 0, repeats: int = 1):
+    nthreads = nthreads or host_cores()
     """the oracle (kind = "port": acados-algorithm restatement, not acados) on the host cores,
     one solve per core via OpenMP"""
     from nmpc_nav_control_b200 import synth
@@ -115,20 +133,20 @@ def cpu_baseline(model: str, sample: int, nthreads: int = 0, repeats: int = 1):
 
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; real acados is
-    not installable here) with all host threads, bounded sample per step."""
+    not installable here) on all host cores of the box, bounded sample per step.
+    Under torchrun rank 0 alone runs it (with every core of the box, whatever OMP_NUM_THREADS says)."""
     rank, world, _ = _dist_env()
     if rank != 0:
         return
-    from oracle import orc
-    cores = orc.max_threads()
-    sample = int(min(BATCH, max(16384, 512 * cores)))
-    cpu_baseline(MODEL, min(sample, 1024))          # warm-up / page-in
+    cores = host_cores()
+    sample = int(min(args.batch, max(16384, 512 * cores)))
+    cpu_baseline(MODEL, min(sample, 1024), nthreads=cores)          # warm-up / page-in
     for _ in range(max(0, args.warmup - 1)):
-        cpu_baseline(MODEL, sample)
+        cpu_baseline(MODEL, sample, nthreads=cores)
     t = []
     r = None
     for _ in range(args.steps):
-        r = cpu_baseline(MODEL, sample)
+        r = cpu_baseline(MODEL, sample, nthreads=cores)
         t.append(r["seconds"])
     sec = float(np.mean(t))
     val = sample / sec
@@ -136,12 +154,105 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_per_step": sample, "robot_model": MODEL},
+        "config": bench_config(args.batch),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": f"{sample} diff instances per step (same generator/seed as the GPU arm), OpenMP one solve per core"},
+                         "sample": f"{sample} diff instances per step (same generator/seed as the GPU arm), OpenMP one solve per core, "
+                                   f"{r['cores']} threads set explicitly"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "latency": cpu_latency(MODEL, 200),
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_latency(model: str, calls: int) -> dict:
+    """one RTI solve on one core through the oracle port (what `{m}_acados_solve` costs the reference per tick)"""
+    from nmpc_nav_control_b200 import synth
+    from nmpc_nav_control_b200.problem import MODELS
+    from oracle import orc
+    spec = MODELS[model]
+    o = orc.Oracle(model, spec.codegen_defaults(), fast=True)
+    inst = synth.make_instances(spec, 0, 1)
+    x0 = inst["x0"].numpy().copy(); yref = inst["yref"].numpy().copy()
+    ts = []
+    for i in range(calls + 20):
+        x = np.zeros((1, spec.n + 1, spec.nx)); u = np.zeros((1, spec.n, spec.nu))
+        t0 = time.perf_counter()
+        o.rti_batch(x0, yref, x, u, nthreads=1)
+        ts.append((time.perf_counter() - t0) * 1e6)
+    ts = np.array(ts[20:])
+    return {"what": "one cold-iterate diff RTI solve, oracle port, 1 thread", "calls": calls,
+            "p50_us": float(np.percentile(ts, 50)), "p95_us": float(np.percentile(ts, 95)), "p99_us": float(np.percentile(ts, 99))}
+
+
+def gpu_latency(model: str, device: int, calls: int = 1000, warm: int = 100) -> dict:
+    """host wall clock around a batch = 1 solve through the C ABI (H2D of x0 / yref, launches, D2H of
+    u_0 / x_1 / status, sync) - what the ROS drop-in sees per tick; cold iterate (the worst case of a tick)"""
+    from nmpc_nav_control_b200 import synth
+    from nmpc_nav_control_b200.problem import MODELS
+    from nmpc_nav_control_b200.solver import BatchedRtiSolver
+    spec = MODELS[model]
+    inst = synth.make_instances(spec, 0, 1, pose_only=True)
+    x0 = inst["x0"].numpy().copy(); yref = inst["yref"].numpy().copy()
+    s = BatchedRtiSolver(spec, 1, device=device)
+    out = None
+    for _ in range(warm):
+        s.reset()
+        out = s.solve_host(x0, yref, out=out)
+    ts = []
+    for _ in range(calls):
+        s.reset()
+        t0 = time.perf_counter()
+        out = s.solve_host(x0, yref, out=out)
+        ts.append((time.perf_counter() - t0) * 1e6)
+    ts = np.array(ts)
+    r = {"what": "batch = 1 cold-iterate diff RTI solve through nmpc_rti_solve_host (C ABI, host buffers)", "calls": calls,
+         "warmup": warm, "p50_us": float(np.percentile(ts, 50)), "p95_us": float(np.percentile(ts, 95)),
+         "p99_us": float(np.percentile(ts, 99)), "qp_iter": int(out["qp_iter"][0])}
+    s.close()
+    return r
+
+
+def fp64_executed(qp_s: float, peak_tflops: float, batch: int):
+    """executed fp64 flops of K3 (ncu smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on summed over the K3 launches
+    of one step, fma x 2; profiles/k3_exec_flops.json, made by tools/ncu_flops.py) / K3 time of THIS run"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_exec_flops.json")) as f:
+            j = json.load(f)
+        if j.get("model") != MODEL or j.get("batch") != batch:
+            return None
+        fl = float(j["flops_per_step"])
+        return {"kernel": "K3", "bound": "fp64", "achieved": fl / qp_s / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": fl / qp_s / 1e12 / peak_tflops if peak_tflops > 0 else None,
+                "note": "executed dadd + dmul + 2 dfma thread instructions (ncu counters of the committed capture, "
+                        "profiles/k3_exec_flops.json) / K3 time of this run; the dense-equivalent figure is roofline_fp64"}
+    except Exception:
+        return None
+
+
+def extra_configs(rank: int, world: int, local: int, barrier) -> dict:
+    """BASELINE configs 3 and 5 under the same clock (short: 2 warm-ups + 3 steps each): omni4 262,144 on one GPU
+    (rank 0 only) and the mixed omni4 / diff / tric 1,048,576-instance batch cut into contiguous shards over the ranks."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_models
+    from nmpc_nav_control_b200.shard import shard_range
+    out = {}
+    if world == 1:
+        r = bench_models.throughput("omni4", 262144, steps=3, warm=2)
+        out["omni4_262144"] = {"value": r["solves_per_s"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "n_gpus": 1,
+                               "mean_qp_iter": r["mean_qp_iter"], "status_nonzero": r["status_nonzero"], "steps": 3}
+    total = 1048576
+    lo, hi = shard_range(total, rank, world)
+    r = bench_models.mixed(hi - lo, steps=3, warm=2, device=local, start=lo // 3, sync=barrier)
+    t = torch.tensor([r["ms_per_step"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out["mixed_1M"] = {"value": total / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+                       "per_gpu": hi - lo, "steps": 3, "status_nonzero": int(sum(r["status_nonzero"].values())),
+                       "timing": "wall clock around barrier + synchronize, max over ranks"}
+    return out
 
 
 def run_ours(args):
@@ -229,6 +340,8 @@ def run_ours(args):
     value = world * B / (ms_step * 1e-3)
     status_bad = int((out["status"] != 0).sum().item())
     mean_iter = float(out["qp_iter"].double().mean().item())
+    hist = torch.bincount(out["qp_iter"].long().clamp(min=0)).cpu().tolist()
+    qp_iter_hist = {str(i): int(c) for i, c in enumerate(hist) if c}
     launches = solver.last_launches() * args.steps
 
     # per-kernel times (second pass, one event read-out per step) for the roofline of K3
@@ -249,10 +362,19 @@ def run_ours(args):
     h2d = B * (spec.nx + (spec.n + 1) * 3) * 8
     d2h = B * (spec.nu + spec.nx) * 8 + B * 8
 
+    solver.close()                       # frees the workspaces before the larger configurations
+    extras = None
+    if not args.no_extra:
+        extras = extra_configs(rank, world, local, barrier)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    latency = None
+    if not args.no_extra:
+        latency = gpu_latency(MODEL, local)
+        if not args.no_cpu:
+            latency["cpu_port"] = cpu_latency(MODEL, 200)
 
     # measured DRAM traffic of K3 per solve (ncu dram__bytes over all K3 launches of one step, see
     # tools/ncu_launches.py --json and profiles/): what the streaming roofline is computed from
@@ -280,8 +402,6 @@ def run_ours(args):
     # CPU baseline (oracle port) on this box's cores, bounded sample
     cpu = None
     if not args.no_cpu:
-        from oracle import orc
-        cores = orc.max_threads()
         sample = BATCH                                  # the whole workload: ~10 s of CPU work for the three passes
         cpu_baseline(MODEL, 1024)
         r = cpu_baseline(MODEL, sample, repeats=3)
@@ -293,11 +413,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "robot_model": MODEL, "batch_per_gpu": B, "N": spec.n, "iterate": "reset (zero) before every step",
-                   "l2": "inputs (131 MB) and the K3 workspace (5.6 GB tile state streamed by every sweep, 3 GB of group records) "
-                         "exceed the 126 MB L2 many times over; no explicit flush",
-                   "k3_schedule": os.environ.get("NMPC_K3", "hybrid"),
-                   "mean_qp_iter": mean_iter, "status_nonzero": status_bad},
+        "config": bench_config(B),
+        "run": {"l2": "inputs (131 MB) and the K3 workspace (GBs of per-instance interior-point records streamed by every sweep) "
+                      "exceed the 126 MB L2 many times over; no explicit flush",
+                "k3_schedule": os.environ.get("NMPC_K3", "default"), "mean_qp_iter": mean_iter, "status_nonzero": status_bad,
+                "qp_iter_hist": qp_iter_hist},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "api": "nmpc_rti_solve_host (C ABI, pinned host buffers)"},
@@ -318,7 +438,10 @@ def run_ours(args):
                           "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,
                           "peak_source": "self-measured DFMA micro-benchmark (MEASURED_PEAKS.json has no fp64 figure)",
                           "note": "achieved = dense-equivalent flops (2.69e5 per IPM iteration, SURVEY 8d) x measured mean iterations"},
+        "roofline_fp64_executed": fp64_executed(qp_s, fp64_peak, B),
         "cpu_baseline": cpu,
+        "latency": latency,
+        "configs": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -333,6 +456,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the latency block and the config 3 / 5 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

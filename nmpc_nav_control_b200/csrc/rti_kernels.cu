@@ -19,6 +19,7 @@
 
 #include "rti_core.cuh"
 #include "rti_group.cuh"
+#include "rti_coop.cuh"
 #include "ctrl_glue.cuh"
 #include "path_disc.cuh"
 #include "rollout.cuh"
@@ -244,6 +245,22 @@ k_ipm_group(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ld
             int* __restrict__ next, GrpOut out, GrpResume rs)
 {
     using GP = Grp<M, G>;
+    extern __shared__ __align__(16) double grp_sm[];
+    typename GP::Lane L;
+    GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
+    GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out, rs);
+}
+
+// K3, coop path (rti_coop.cuh): the same persistent schedule and records, lanes cooperating through shuffles
+#ifndef NMPC_COOP_MINB
+#define NMPC_COOP_MINB 3
+#endif
+template <class M, int G, int MINB>
+__global__ void __launch_bounds__(GRP_WARPS * 32, MINB)
+k_ipm_coop(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldWe, IpmOpts o, double* __restrict__ ws,
+           int* __restrict__ next, GrpOut out, GrpResume rs)
+{
+    using GP = Coop<M, G>;
     extern __shared__ __align__(16) double grp_sm[];
     typename GP::Lane L;
     GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
@@ -615,6 +632,7 @@ struct nmpc_solver {
     double *d_ws_g = nullptr;    // group workspace (schedules 1, 2)
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
+    int k3_impl = 1;             // lane-group kernel: 0 first mapping (rti_group.cuh), 1 lane-cooperative mapping (rti_coop.cuh)
     int hyb_kmax = 12; double hyb_frac = 0.6;   // hand over once fewer than 60 % of the chunk iterate (sweep in profiles/README_r01_notes.txt)
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
@@ -730,6 +748,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
     if (const char* e = getenv("NMPC_HYB_MIN")) { int v = atoi(e); if (v >= 0) s->hyb_min = v; }
     if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
+    if (const char* e = getenv("NMPC_GRP_IMPL")) s->k3_impl = !strcmp(e, "group") ? 0 : 1;
     s->grp_G = (model == 1) ? 16 : 8;
     if (const char* e = getenv("NMPC_GRP_G")) { int v = atoi(e); if ((v == 8 && model != 1) || v == 16 || v == 32) s->grp_G = v; }
     {
@@ -901,17 +920,17 @@ static int ensure_events(nmpc_solver* s, int nchunks)
 }
 
 // ---- group path: one persistent launch per chunk ------------------------------------------------
-template <class M, int G, int MINB>
-static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
-                        const GrpOut& out, const GrpResume& rs, cudaStream_t st)
+typedef void (*grp_kernel_t)(int, int, Tables, const double*, int, IpmOpts, double*, int*, GrpOut, GrpResume);
+template <class GP>
+static int launch_group_k(nmpc_solver* s, grp_kernel_t kern, int i0, int n, const Tables& tb, const double* d_We, int ldWe,
+                          const IpmOpts& o, const GrpOut& out, const GrpResume& rs, cudaStream_t st)
 {
-    using GP = Grp<M, G>;
     const size_t smem = (size_t)GRP_WARPS * GP::WARP_D * sizeof(double);
     int& blocks_per_sm = s->grp_blocks_per_sm;
     if (!blocks_per_sm) {
-        CK(cudaFuncSetAttribute(k_ipm_group<M, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ipm_group<M, G, MINB>, GRP_WARPS * 32, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, GRP_WARPS * 32, smem));
         if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_group does not fit on an SM");
         if (const char* e = getenv("NMPC_GRP_BPS")) { int v = atoi(e); if (v >= 1 && v < nb) nb = v; }
         blocks_per_sm = nb;
@@ -925,9 +944,15 @@ static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const d
     s->grp_blocks = blocks;
     int* queue = s->d_cnt + s->cnt_cap - 1;
     CK(cudaMemsetAsync(queue, 0, sizeof(int), st));
-    k_ipm_group<M, G, MINB><<<blocks, GRP_WARPS * 32, smem, st>>>(i0, n, tb, d_We, ldWe, o, s->d_ws_g, queue, out, rs);
+    kern<<<blocks, GRP_WARPS * 32, smem, st>>>(i0, n, tb, d_We, ldWe, o, s->d_ws_g, queue, out, rs);
     CK(cudaGetLastError());
     return 0;
+}
+template <class M, int G, int MINB>
+static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
+                        const GrpOut& out, const GrpResume& rs, cudaStream_t st)
+{
+    return launch_group_k<Grp<M, G>>(s, k_ipm_group<M, G, MINB>, i0, n, tb, d_We, ldWe, o, out, rs, st);
 }
 
 template <class M>
@@ -936,6 +961,8 @@ static int launch_group_any(nmpc_solver* s, int i0, int n, const Tables& tb, con
 {
     using S = Rti<M>;
     const int G = s->grp_G;
+    if (s->k3_impl == 1)       // lane-cooperative mapping (rti_coop.cuh): G = 4 nv lanes per instance
+        return launch_group_k<Coop<M, 4 * S::NV>>(s, k_ipm_coop<M, 4 * S::NV, NMPC_COOP_MINB>, i0, n, tb, d_We, ldWe, o, out, rs, st);
     if constexpr (S::NV == 2) {
         if (G == 8) return launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
         if (G == 16) return launch_group<M, 16, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
