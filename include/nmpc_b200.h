@@ -98,6 +98,24 @@ int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const do
                           const double* d_We, double* d_x, double* d_u, int ldxu,
                           int* d_status, int* d_qp_iter, double* d_stats, void* stream);
 
+/* ---- BASELINE config 4 / north-star kernel (4): warm-start shift and SQP to convergence ---------
+ * The reference never shifts and does one RTI per tick (NMPCNavControlROS.cpp:309,316,326 ->
+ * NMPCNavControlDiff.cpp:142); the shapes mirrored here are its simulation scripts: the explicit warm start from the
+ * previous solution (scripts/test_scripts/casadi_sim_diff.py:104-106) and the closed loop of
+ * scripts/test_scripts/acados_sim_diff.py:119-163.
+ * nmpc_shift_device: x_k <- x_{k+1} (k < N), x_N kept; u_k <- u_{k+1} (k < N-1), u_{N-1} kept.
+ *   d_x, d_u NULL = the persisted iterate; d_mask [B] (int) or NULL: only instances with a non-zero entry shift.
+ * nmpc_sqp_solve_device: per instance, repeats the RTI step (same arguments as nmpc_rti_solve_device) until the inf-norm
+ *   of its step (dx, du over all stages) is <= tol, its status is non-zero, or max_iter steps were taken.  A device-side
+ *   mask keeps the instances that stopped out of the following passes (their queue is rebuilt on the device before every
+ *   pass); all max_iter passes are enqueued, nothing synchronises with the host.
+ *   d_status [B]: status of the instance's last step; d_sqp_iter [B] or NULL: RTI steps taken; d_qp_iter [B] or NULL:
+ *   interior-point iterations summed over them. */
+int nmpc_shift_device(nmpc_solver* s, int B, double* d_x, double* d_u, int ldxu, const int* d_mask, void* stream);
+int nmpc_sqp_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
+                          double* d_x, double* d_u, int ldxu, int max_iter, double tol, int* d_status, int* d_sqp_iter,
+                          int* d_qp_iter, void* stream);
+
 /* ---- host-buffer call (what a controller process would bind): instance-major host arrays ---
  *   x0bar [B][nx], yref [B][N+1][nyref], We [B][nx] or NULL   -> copied H2D and transposed on device
  *   u0 [B][nu], x1 [B][nx], status [B], qp_iter [B]            <- copied D2H (what run() reads, Diff.cpp:151-169)
@@ -127,6 +145,10 @@ int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double
 int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
                           const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd,
                           int* d_status, int* d_qp_iter, void* stream);
+/* the same tick with SQP to convergence in place of the single RTI step (sqp_max_iter, sqp_tol as nmpc_sqp_solve_device) */
+int nmpc_ctrl_tick_sqp_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                              const double* d_refs, const int* d_nref, int nref_max, double dt, int sqp_max_iter, double sqp_tol,
+                              double* d_cmd, int* d_status, int* d_qp_iter, void* stream);
 int nmpc_ctrl_reset(nmpc_solver* s, void* stream);
 int nmpc_ctrl_state_device(nmpc_solver* s, double** d_vref, int* leading_dim);
 /* host-buffer form: pose [B][3], vel [B][3], steer [B] or NULL, refs [B][nref_max][3] (nref_max <= N+1), nref [B] or
@@ -176,6 +198,30 @@ int nmpc_plant_step_device(nmpc_solver* s, int B, double dt, const double* d_noi
                            double* d_vel, double* d_steer, void* stream);
 int nmpc_path_nearest_device(int device, int B, const double* d_segments, const int* d_path_offsets, int n_paths,
                              const int* d_path_id, const double* d_pose, double back, double ahead, double* d_u, void* stream);
+
+/* nmpc_rollout_device: the whole closed loop for B robots, `ticks` ticks enqueued by ONE call with nothing between them on
+ * the host.  Per tick, in the order of NMPCNavControlROS::processFollowPath (NMPCNavControlROS.cpp:648-720): nearest
+ * path parameter -> N+1 reference poses -> controller tick (one RTI step, or SQP to convergence) -> nominal plant step
+ * (scripts/test_scripts/acados_sim_diff.py:136-160) -> optional warm-start shift of the iterate.
+ *   d_u [B]                  path parameter per robot, in/out
+ *   d_xplant [nx][B], d_pose [3][B], d_vel [3][B], d_steer [B] (tric; else NULL)    plant state and measurements, in/out
+ *   d_noise [ticks][nu][B] or NULL      added to u_0 in the plant (drawn and seeded by the caller)
+ *   d_traj [ticks+1][3][B] or NULL      out: pose before the first tick and after every tick
+ *   d_cmds [ticks][3][B] or NULL        out: velocity commands
+ *   d_nfail [ticks] (int) or NULL       out: robots whose solve returned a non-zero status, per tick
+ * The controller state (carried reference states, iterate) is the solver's: nmpc_ctrl_reset / nmpc_reset start a run. */
+typedef struct {
+    double dt;              /* controller period = sample period of the reference poses                        */
+    double back, ahead;     /* nearest-point search window (path-parameter units), see nmpc_path_nearest_device */
+    double sqp_tol;         /* SQP: step inf-norm at which an instance stops iterating                          */
+    int is_holonomic;       /* PathDiscretizer flag (the node passes false)                                     */
+    int sqp_max_iter;       /* 1 = one RTI step per tick (the reference); > 1 = SQP to convergence              */
+    int shift;              /* 1 = shift the iterate one stage after every tick (the reference: 0)              */
+} nmpc_rollout_opts;
+int nmpc_rollout_device(nmpc_solver* s, int B, int ticks, const nmpc_rollout_opts* o, const double* d_segments,
+                        const int* d_path_offsets, int n_paths, const int* d_path_id, double* d_u, double* d_xplant,
+                        double* d_pose, double* d_vel, double* d_steer, const double* d_noise, double* d_traj, double* d_cmds,
+                        int* d_nfail, void* stream);
 
 /* statistics of the last nmpc_rti_solve_host call, stats [8][B] (rows as d_stats above), host pointer */
 int nmpc_last_stats_host(nmpc_solver* s, int B, double* stats);

@@ -19,6 +19,7 @@ SYMBOLS = [
     "nmpc_dfma_peak_tflops",
     "nmpc_ctrl_tick_device", "nmpc_ctrl_reset", "nmpc_ctrl_state_device", "nmpc_ctrl_tick_host",
     "nmpc_path_discretize_device", "nmpc_plant_step_device", "nmpc_path_nearest_device",
+    "nmpc_shift_device", "nmpc_sqp_solve_device", "nmpc_ctrl_tick_sqp_device", "nmpc_rollout_device",
 ]
 
 
@@ -27,6 +28,12 @@ class IpmOpts(C.Structure):
                 ("mu0", "alpha_min", "res_g_max", "res_b_max", "res_d_max", "res_m_max",
                  "reg_prim", "lam_min", "t_min", "tau_min", "thr0")] + \
                [("iter_max", C.c_int), ("cond_pred_corr", C.c_int)]
+
+
+class RolloutOpts(C.Structure):
+    """nmpc_rollout_opts of include/nmpc_b200.h"""
+    _fields_ = [("dt", C.c_double), ("back", C.c_double), ("ahead", C.c_double), ("sqp_tol", C.c_double),
+                ("is_holonomic", C.c_int), ("sqp_max_iter", C.c_int), ("shift", C.c_int)]
 
 
 class Dims(C.Structure):
@@ -73,6 +80,10 @@ def load() -> C.CDLL:
         lib.nmpc_path_discretize_device.argtypes = [C.c_int, C.c_int, dp, ip, C.c_int, ip, dp, C.c_double, C.c_int, C.c_int, dp, vp]
         lib.nmpc_plant_step_device.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, dp, vp]
         lib.nmpc_path_nearest_device.argtypes = [C.c_int, C.c_int, dp, ip, C.c_int, ip, dp, C.c_double, C.c_double, dp, vp]
+        lib.nmpc_shift_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, ip, vp]
+        lib.nmpc_sqp_solve_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, dp, dp, C.c_int, C.c_int, C.c_double, ip, ip, ip, vp]
+        lib.nmpc_ctrl_tick_sqp_device.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, C.c_int, C.c_double, dp, ip, ip, vp]
+        lib.nmpc_rollout_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(RolloutOpts), dp, ip, C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp, ip, vp]
         lib.nmpc_ctrl_reset.argtypes = [vp, vp]
         lib.nmpc_ctrl_state_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
         lib.nmpc_ctrl_tick_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, ip, C.c_int, C.c_double, dp, ip, ip]

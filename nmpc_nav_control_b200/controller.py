@@ -48,6 +48,7 @@ class BatchedNavController:
         self.solver.set_tables(W=np.tile(W_diag, (n, 1)), We=W_diag[:s.nx].copy(), p=tile(p, s.p),
                                lbx=tile(x_min, s.lbx), ubx=tile(x_max, s.ubx), lbu=tile(u_min, s.lbu), ubu=tile(u_max, s.ubu))
         self._steer = None
+        self._zero_steer = None
         _lib.check(self.lib.nmpc_ctrl_reset(self.solver._h, None), "nmpc_ctrl_reset")
         torch.cuda.synchronize(self.tdev)
 
@@ -75,8 +76,10 @@ class BatchedNavController:
 
     # ---- device tick: SoA CUDA tensors -------------------------------------------------------
     def run(self, pose: torch.Tensor, vel: torch.Tensor, traj_ref: torch.Tensor, nref: torch.Tensor | None = None,
-            cmd: torch.Tensor | None = None, out: dict | None = None, stream: torch.cuda.Stream | None = None):
+            cmd: torch.Tensor | None = None, out: dict | None = None, stream: torch.cuda.Stream | None = None,
+            sqp_max_iter: int = 1, sqp_tol: float = 0.0):
         """pose [3,B], vel [3,B] (v, vn, w), traj_ref [nref_max,3,B], nref [B] int32 or None (= nref_max);
+        sqp_max_iter > 1: SQP to convergence instead of the reference's single RTI step (BASELINE config 4);
         returns dict(cmd [3,B], status [B], qp_iter [B]) of CUDA tensors; asynchronous."""
         B = pose.shape[1]
         nref_max = traj_ref.shape[0]
@@ -85,9 +88,13 @@ class BatchedNavController:
         assert pose.shape == (3, B) and vel.shape == (3, B) and traj_ref.shape == (nref_max, 3, B)
         if nref is not None:
             assert nref.is_cuda and nref.dtype == torch.int32 and nref.shape == (B,)
+        st = stream if stream is not None else torch.cuda.current_stream(self.tdev)
         steer = self._steer
         if steer is None and self.spec.name == "tric":
-            steer = torch.zeros(B, dtype=torch.float64, device=self.tdev)      # the wrapper's initial angle, Tric.cpp:14
+            if self._zero_steer is None or self._zero_steer.shape[0] < B:      # the wrapper's initial angle, Tric.cpp:14
+                self._zero_steer = torch.zeros(self.solver.max_batch, dtype=torch.float64, device=self.tdev)
+                torch.cuda.current_stream(self.tdev).synchronize()              # persistent buffer: usable on any stream afterwards
+            steer = self._zero_steer[:B]
         if steer is not None and not isinstance(steer, torch.Tensor):
             steer = torch.as_tensor(np.asarray(steer, dtype=np.float64), device=self.tdev)
         if steer is not None:
@@ -96,10 +103,15 @@ class BatchedNavController:
             out = dict(cmd=torch.zeros(3, B, dtype=torch.float64, device=self.tdev) if cmd is None else cmd,
                        status=torch.empty(B, dtype=torch.int32, device=self.tdev),
                        qp_iter=torch.empty(B, dtype=torch.int32, device=self.tdev))
-        st = stream if stream is not None else torch.cuda.current_stream(self.tdev)
-        _lib.check(self.lib.nmpc_ctrl_tick_device(self.solver._h, B, _ptr(pose), _ptr(vel), _ptr(steer), _ptr(traj_ref),
-                                                  _ptr(nref), nref_max, self.dt, _ptr(out["cmd"]), _ptr(out["status"]),
-                                                  _ptr(out["qp_iter"]), C.c_void_p(st.cuda_stream)), "nmpc_ctrl_tick_device")
+        if sqp_max_iter > 1:
+            _lib.check(self.lib.nmpc_ctrl_tick_sqp_device(self.solver._h, B, _ptr(pose), _ptr(vel), _ptr(steer), _ptr(traj_ref),
+                                                          _ptr(nref), nref_max, C.c_double(self.dt), int(sqp_max_iter), C.c_double(sqp_tol),
+                                                          _ptr(out["cmd"]), _ptr(out["status"]), _ptr(out["qp_iter"]),
+                                                          C.c_void_p(st.cuda_stream)), "nmpc_ctrl_tick_sqp_device")
+        else:
+            _lib.check(self.lib.nmpc_ctrl_tick_device(self.solver._h, B, _ptr(pose), _ptr(vel), _ptr(steer), _ptr(traj_ref),
+                                                      _ptr(nref), nref_max, self.dt, _ptr(out["cmd"]), _ptr(out["status"]),
+                                                      _ptr(out["qp_iter"]), C.c_void_p(st.cuda_stream)), "nmpc_ctrl_tick_device")
         return out
 
     # ---- host tick: instance-major numpy arrays ------------------------------------------------

@@ -12,6 +12,7 @@
 //   * status: 0 ok, 1 NaN, 2 max iter (not produced by RTI), 3 min step, 4 QP failure
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,14 +31,21 @@ struct nmpc_acados_core {
     // host staging (what the setters write)
     std::vector<double> W, We, lbx, ubx, lbu, ubu, p;      // tables, layout of nmpc_set_*
     std::vector<double> lbx0, ubx0, yref;                   // stage-0 state bounds; yref [N+1][ny]
-    bool w_dirty, b_dirty, p_dirty, w_bad;
-    // host copy of the iterate after the last solve / reset / create
+    bool w_dirty, b_dirty, p_dirty;
+    std::vector<unsigned char> w_bad;                       // per stage: the last W set for it was not diagonal
+    // host copy of the iterate after the last solve / reset / create; after a solve only x_0, x_1 and u_0 are current
+    // (what run() reads, Diff.cpp:145-152), the rest is fetched from the device on the first request for another stage
     std::vector<double> x, u;
+    bool iter_stale;
     double time_tot;
     int qp_iter, status;
 };
 
-static void fetch_iterate(nmpc_acados_core* c) { nmpc_get_iterate_host(c->s, 1, c->x.data(), c->u.data()); }
+static void fetch_iterate(nmpc_acados_core* c)
+{
+    nmpc_get_iterate_host(c->s, 1, c->x.data(), c->u.data());
+    c->iter_stale = false;
+}
 
 extern "C" nmpc_acados_core* nmpc_acados_core_create(int model)
 {
@@ -46,7 +54,9 @@ extern "C" nmpc_acados_core* nmpc_acados_core_create(int model)
     nmpc_acados_core* c = new (std::nothrow) nmpc_acados_core();
     if (!c) return nullptr;
     c->model = model; c->d = d; c->s = nullptr;
-    if (nmpc_create(model, 1, 0, &c->s) != 0) { delete c; return nullptr; }   // no device -> create fails, no CPU fallback
+    int device = 0;
+    if (const char* e = std::getenv("NMPC_ACADOS_DEVICE")) device = std::atoi(e);
+    if (nmpc_create(model, 1, device, &c->s) != 0) { delete c; return nullptr; }   // no device -> create fails, no CPU fallback
     const int n = d.n;
     c->W.resize((size_t)n * d.ny); c->We.resize(d.nx);
     c->lbx.resize((size_t)n * d.nbx); c->ubx.resize((size_t)n * d.nbx);
@@ -58,8 +68,9 @@ extern "C" nmpc_acados_core* nmpc_acados_core_create(int model)
     c->lbx0.assign(c->x.begin(), c->x.begin() + d.nx);      // constraints.x0 default (generate_c_code.py:58-60)
     c->ubx0 = c->lbx0;
     c->yref.assign((size_t)(n + 1) * d.ny, 0.0);
-    c->w_dirty = c->b_dirty = c->p_dirty = c->w_bad = false;
-    c->time_tot = 0.0; c->qp_iter = 0; c->status = 0;
+    c->w_dirty = c->b_dirty = c->p_dirty = false;
+    c->w_bad.assign((size_t)n + 1, 0);
+    c->time_tot = 0.0; c->qp_iter = 0; c->status = 0; c->iter_stale = false;
     c->cfg.core = c; c->in.core = c; c->out.core = c; c->out.inf_norm_res = 0.0; c->solver.core = c;
     c->dims.core = c; c->dims.N = n; c->dims.nx = d.nx; c->dims.nu = d.nu; c->dims.ny = d.ny; c->dims.nyn = d.nyn;
     c->dims.np = d.np; c->dims.nbx = d.nbx; c->dims.nbu = d.nbu;
@@ -93,6 +104,7 @@ extern "C" int nmpc_acados_core_reset(nmpc_acados_core* c, int)
     if (nmpc_reset(c->s) != 0) return 1;
     std::fill(c->x.begin(), c->x.end(), 0.0);
     std::fill(c->u.begin(), c->u.end(), 0.0);
+    c->iter_stale = false;
     return 0;
 }
 
@@ -100,18 +112,26 @@ extern "C" int nmpc_acados_core_solve(nmpc_acados_core* c)
 {
     const auto t0 = std::chrono::steady_clock::now();
     const nmpc_dims_t& d = c->d;
-    if (c->w_bad) return NMPC_QP_FAILURE;                       // a non-diagonal W was set
+    for (unsigned char b : c->w_bad)
+        if (b) return NMPC_QP_FAILURE;                          // a stage holds a non-diagonal W
     for (int j = 0; j < d.nx; j++)
         if (c->lbx0[j] != c->ubx0[j]) return NMPC_QP_FAILURE;   // stage 0 must be the x0 equality
-    if (c->w_dirty && nmpc_set_weights(c->s, c->W.data(), c->We.data()) != 0) return NMPC_QP_FAILURE;
+    // the terminal weight changes every tick in the diff wrapper (Diff.cpp:126-139): it travels as the per-instance
+    // W_e argument of the solve, so only a change of a path-stage W touches the device tables
+    if (c->w_dirty && nmpc_set_weights(c->s, c->W.data(), nullptr) != 0) return NMPC_QP_FAILURE;
     if (c->b_dirty && nmpc_set_bounds(c->s, c->lbx.data(), c->ubx.data(), c->lbu.data(), c->ubu.data()) != 0) return NMPC_QP_FAILURE;
     if (c->p_dirty && nmpc_set_params(c->s, c->p.data()) != 0) return NMPC_QP_FAILURE;
     c->w_dirty = c->b_dirty = c->p_dirty = false;
     double u0[4], x1[11];
     int status = 0, qp_iter = 0;
-    if (nmpc_rti_solve_host(c->s, 1, c->lbx0.data(), c->yref.data(), d.ny, nullptr, u0, x1, &status, &qp_iter) != 0)
+    if (nmpc_rti_solve_host(c->s, 1, c->lbx0.data(), c->yref.data(), d.ny, c->We.data(), u0, x1, &status, &qp_iter) != 0)
         return NMPC_QP_FAILURE;
-    fetch_iterate(c);
+    if (status == 0) {
+        std::memcpy(c->x.data(), c->lbx0.data(), sizeof(double) * d.nx);       // K4: x_0 <- the measured state
+        std::memcpy(c->x.data() + d.nx, x1, sizeof(double) * d.nx);
+        std::memcpy(c->u.data(), u0, sizeof(double) * d.nu);
+    }
+    c->iter_stale = true;
     double stats[8];
     c->out.inf_norm_res = 0.0;
     if (nmpc_last_stats_host(c->s, 1, stats) == 0)
@@ -158,14 +178,14 @@ extern "C" int ocp_nlp_cost_model_set(ocp_nlp_config*, ocp_nlp_dims*, ocp_nlp_in
     if (is(field, "W")) {
         double* dst = stage < d.n ? &c->W[(size_t)stage * d.ny] : c->We.data();
         bool bad = false;
-        for (int j = 0; j < ny; j++)
-            for (int i = 0; i < ny; i++) {
-                if (i == j) dst[i] = v[i + (size_t)ny * j];
-                else if (v[i + (size_t)ny * j] != 0.0) bad = true;
-            }
-        if (bad) c->w_bad = true;
-        c->w_dirty = true;
-        return bad ? 1 : 0;
+        for (int j = 0; j < ny && !bad; j++)
+            for (int i = 0; i < ny; i++)
+                if (i != j && v[i + (size_t)ny * j] != 0.0) { bad = true; break; }
+        c->w_bad[stage] = bad ? 1 : 0;                           // a later diagonal W for the stage clears it
+        if (bad) return 1;                                       // nothing of a rejected W is stored
+        for (int j = 0; j < ny; j++) dst[j] = v[j + (size_t)ny * j];
+        if (stage < d.n) c->w_dirty = true;
+        return 0;
     }
     if (is(field, "yref") || is(field, "y_ref")) {
         double* dst = &c->yref[(size_t)stage * d.ny];
@@ -180,8 +200,13 @@ extern "C" void ocp_nlp_out_get(ocp_nlp_config*, ocp_nlp_dims*, ocp_nlp_out* out
     if (!out || !out->core || !field || !value) return;
     nmpc_acados_core* c = out->core;
     const nmpc_dims_t& d = c->d;
-    if (is(field, "x") && stage >= 0 && stage <= d.n) std::memcpy(value, &c->x[(size_t)stage * d.nx], sizeof(double) * d.nx);
-    else if (is(field, "u") && stage >= 0 && stage < d.n) std::memcpy(value, &c->u[(size_t)stage * d.nu], sizeof(double) * d.nu);
+    if (is(field, "x") && stage >= 0 && stage <= d.n) {
+        if (c->iter_stale && (stage > 1 || c->status != 0)) fetch_iterate(c);
+        std::memcpy(value, &c->x[(size_t)stage * d.nx], sizeof(double) * d.nx);
+    } else if (is(field, "u") && stage >= 0 && stage < d.n) {
+        if (c->iter_stale && (stage > 0 || c->status != 0)) fetch_iterate(c);
+        std::memcpy(value, &c->u[(size_t)stage * d.nu], sizeof(double) * d.nu);
+    }
 }
 
 extern "C" void ocp_nlp_get(ocp_nlp_solver* solver, const char* field, void* return_value_)

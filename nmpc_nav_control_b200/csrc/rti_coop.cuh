@@ -36,6 +36,16 @@
 #define CO_PHASE_END_NS } }
 #endif
 #define CO_UNROLL _Pragma("unroll")
+// the pose rows of [A B] and the lag constants of a stage for the Riccati phases: register copies (16-byte loads, fewer
+// shared-memory instructions, ~60 more live registers) or read where used
+#ifndef NMPC_COOP_EREG
+#define NMPC_COOP_EREG 0
+#endif
+#if NMPC_COOP_EREG
+#define CO_LOAD_E(rec, ltk) double Ef[EP], lt[4 * NV]; ldv(Ef, (rec) + R::E); ldv(lt, (ltk));
+#else
+#define CO_LOAD_E(rec, ltk) const double* Ef = (rec) + R::E; const double* lt = (ltk);
+#endif
 
 // butterfly all-reduce of the array field A[0..n) over the G lanes of a group; T is a scratch field of the same shape.
 // OP(x, y) combines; the result is left in A on every lane (bitwise identical on all lanes: the tree is symmetric).
@@ -124,7 +134,7 @@ struct Coop {
         double zu[NV], gu[NV], dgu[NV];
         double Mxx[NX], Mux[NV], Kc[NV], lh[NV];
         double c4[4], cs[4];
-        double pp[3], pq[3], sp[NV], sq[NV];
+        double pp[3], pq[3], rd[NV + 3], rq[NV + 3];
         double dx, dxs, dxp, du[NV];
         double dp, gt, gs2;
         double nr[6], nq[6];      // ng, nb, nd, nm, lru (max) and musum (sum) / alpha, S0, S1, S2
@@ -187,9 +197,10 @@ struct Coop {
         L.pv = L.xn = L.zn = L.g = L.dg = L.gxt = L.tt = L.e0 = L.e1 = L.e2 = 0.0;
         L.dx = L.dxs = L.dxp = L.dp = L.gt = L.gs2 = 0.0; L.aN = 1.0; L.aD = -1.0;
         for (int i = 0; i < NX; i++) { L.Pc[i] = 0.0; L.Mxx[i] = 0.0; }
-        for (int a = 0; a < NV; a++) { L.zu[a] = L.gu[a] = L.dgu[a] = L.Mux[a] = L.Kc[a] = L.lh[a] = L.sp[a] = L.sq[a] = L.du[a] = 0.0; }
+        for (int a = 0; a < NV; a++) { L.zu[a] = L.gu[a] = L.dgu[a] = L.Mux[a] = L.Kc[a] = L.lh[a] = L.du[a] = 0.0; }
         for (int q = 0; q < 4; q++) { L.c4[q] = L.cs[q] = 0.0; }
         for (int q = 0; q < 3; q++) { L.pp[q] = L.pq[q] = 0.0; }
+        for (int q = 0; q < NV + 3; q++) { L.rd[q] = L.rq[q] = 0.0; }
         for (int q = 0; q < 6; q++) { L.nr[q] = L.nq[q] = 0.0; }
     }
 
@@ -428,8 +439,9 @@ struct Coop {
                 const double* rec = Img<SW_B>::a(img);
                 const double* ltk = sm + L.to + slot * TROW;
                 if (L.isx) {
-                    double rbv[NXP], Ef[EP], lt[4 * NV];
-                    ldv(rbv, scr + O_RBV); ldv(Ef, rec + R::E); ldv(lt, ltk);
+                    double rbv[NXP];
+                    ldv(rbv, scr + O_RBV);
+                    CO_LOAD_E(rec, ltk)
                     double t0 = L.pv, t1 = 0.0;
 #pragma unroll
                     for (int m = 0; m < NX; m++) { if (m & 1) t1 += L.Pc[m] * rbv[m]; else t0 += L.Pc[m] * rbv[m]; }
@@ -446,8 +458,9 @@ struct Coop {
                 const double* img = scr + O_IN + slot * ISZ;
                 const double* rec = Img<SW_B>::a(img);
                 const double* ltk = sm + L.to + slot * TROW;
-                double tv[NXP], Ef[EP], lt[4 * NV];
-                ldv(tv, scr + O_TV); ldv(Ef, rec + R::E); ldv(lt, ltk);
+                double tv[NXP];
+                ldv(tv, scr + O_TV);
+                CO_LOAD_E(rec, ltk)
                 if (hasX && L.isx) {
                     double col[NXP];
                     ldv(col, scr + O_Y + L.r * YS);
@@ -579,32 +592,38 @@ struct Coop {
             GRP_PHASE_BEGIN(lanes)
                 begin_stage<KIND, 1>(L);
             GRP_PHASE_END
-            // ---- F1: prefetch; partial products of K dx ----------------------------------------------------------
+            // ---- F1: prefetch; partial products of K dx and of the pose rows of [A B] [dx; .]; remote dx values ------
             GRP_PHASE_BEGIN(lanes)
                 prefetch<KIND, 1>(L, sm, D - 1, pslot, pvalid);
                 const double* rec = Img<KIND>::a(sm + L.so + O_IN + slot * ISZ);
+                double e0, e1, e2;
+                own_ecol(L, rec + R::E, e0, e1, e2);
+                const double dxm = L.isx ? L.dx : 0.0;
 #pragma unroll
-                for (int a = 0; a < NV; a++) L.sp[a] = (hasU && hasX && L.isx) ? rec[R::KH + a * NX + L.r] * L.dx : 0.0;
+                for (int a = 0; a < NV; a++) L.rd[a] = (hasU && hasX && L.isx) ? rec[R::KH + a * NX + (L.isx ? L.r : 0)] * dxm : 0.0;
+                L.rd[NV] = e0 * dxm; L.rd[NV + 1] = e1 * dxm; L.rd[NV + 2] = e2 * dxm;
+                L.dxs = CO_SHFL(dx, L.csrc);
+                L.dxp = CO_SHFL(dx, L.pf);
             CO_PHASE_END_NS
-            CO_ALLRED(sp, sq, NV, CO_ADD)
-            // ---- F2: du (every lane); one constraint per lane: ratio test, mu sums; step stores; pose partials -------
+            CO_ALLRED(rd, rq, NV + 3, CO_ADD)
+            // ---- F2: du (every lane); one constraint per lane: ratio test, mu sums; step stores; next dx (row r) -------
             GRP_PHASE_BEGIN(lanes)
                 const double* img = sm + L.so + O_IN + slot * ISZ;
                 const double* rec = Img<KIND>::a(img); const double* rec2 = Img<KIND>::b(img);
+                const double* ltk = sm + L.to + slot * TROW;
 #pragma unroll
                 for (int a = 0; a < NV; a++) L.du[a] = 0.0;
                 if (hasU) {
 #pragma unroll
                     for (int a = NV - 1; a >= 0; a--) {
-                        double sacc = -(rec[(DELTA ? R::LHD : R::LH) + a] + L.sp[a]);
+                        double sacc = -(rec[(DELTA ? R::LHD : R::LH) + a] + L.rd[a]);
 #pragma unroll
                         for (int b = a + 1; b < NV; b++) sacc -= rec[R::LUU + b * (b + 1) / 2 + a] * L.du[b];
                         L.du[a] = sacc * rec[R::LUU + a * (a + 1) / 2 + a];
                     }
                 }
-                L.dxs = CO_SHFL(dx, L.csrc);
-                L.dxp = CO_SHFL(dx, L.pf);
-                if (L.is_u ? hasU : hasX) {
+                {
+                    const bool act = L.is_u ? hasU : hasX;
                     const int c = L.cidx;
                     double dzw = L.is_u ? pick(L.du, L.ua) : L.dxs;
                     if (DELTA) dzw += rec2[R::DZA + L.zoff];
@@ -615,48 +634,36 @@ struct Coop {
                     if (DELTA) rm += mcw * rec2[R::MC + c] - L.sigmu;
                     const double dt = sg * dzw - rd;
                     const double dl = -(lam * dt + rm) / t;
-                    if (!DELTA && L.run) L.grec[R::MC + c] = dt * dl;
-                    if (L.aN * dl < lam * L.aD) { L.aN = lam; L.aD = dl; }
-                    if (L.aN * dt < t * L.aD) { L.aN = t; L.aD = dt; }
-                    L.nr[1] += lam * t;
-                    L.nr[2] += lam * dt + t * dl;
-                    L.nr[3] += dl * dt;
+                    if (!DELTA && act && L.run) L.grec[R::MC + c] = dt * dl;
+                    if (act && L.aN * dl < lam * L.aD) { L.aN = lam; L.aD = dl; }
+                    if (act && L.aN * dt < t * L.aD) { L.aN = t; L.aD = dt; }
+                    L.nr[1] += act ? lam * t : 0.0;
+                    L.nr[2] += act ? lam * dt + t * dl : 0.0;
+                    L.nr[3] += act ? dl * dt : 0.0;
                 }
-                double e0, e1, e2;
-                own_ecol(L, rec + R::E, e0, e1, e2);
-                L.pp[0] = L.pp[1] = L.pp[2] = 0.0;
-                if (L.isx) {
-                    if (L.run) {
-                        if (!DELTA) L.grec[R::DZA + NU + L.r] = L.dx;
-                        else L.grec[R::DZ + NU + L.r] = L.dx + rec2[R::DZA + NU + L.r];
-                    }
-                    L.pp[0] = e0 * L.dx; L.pp[1] = e1 * L.dx; L.pp[2] = e2 * L.dx;
+                if (L.run && L.isx) {
+                    if (!DELTA) L.grec[R::DZA + NU + L.r] = L.dx;
+                    else L.grec[R::DZ + NU + L.r] = L.dx + rec2[R::DZA + NU + L.r];
                 }
                 if (L.run && L.r < NV) {
                     const double duo = pick(L.du, L.r);
                     if (!DELTA) L.grec[R::DZA + L.r] = duo;
                     else L.grec[R::DZ + L.r] = duo + rec2[R::DZA + L.r];
                 }
-            CO_PHASE_END_NS
-            if (!hasU) continue;
-            CO_ALLRED(pp, pq, 3, CO_ADD)
-            // ---- F3: next dx, row r --------------------------------------------------------------------------------
-            GRP_PHASE_BEGIN(lanes)
-                if (!L.isx) continue;
-                const double* rec = Img<KIND>::a(sm + L.so + O_IN + slot * ISZ);
-                const double* ltk = sm + L.to + slot * TROW;
-                double ps[3];
+                if (hasU) {
+                    double ps[3];
 #pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    double sacc = L.pp[i];
+                    for (int i = 0; i < 3; i++) {
+                        double sacc = L.rd[NV + i];
 #pragma unroll
-                    for (int a = 0; a < NV; a++) sacc += rec[R::E + i * NC + 1 + 2 * NV + a] * L.du[a];
-                    ps[i] = sacc;
+                        for (int a = 0; a < NV; a++) sacc += rec[R::E + i * NC + 1 + 2 * NV + a] * L.du[a];
+                        ps[i] = sacc;
+                    }
+                    const double psel = L.r == 0 ? ps[0] : L.r == 1 ? ps[1] : L.r == 2 ? ps[2] : 0.0;
+                    double xn = psel + ltk[L.ksf] * L.dx + ltk[L.kpf] * L.dxp + ltk[L.kuf] * pick(L.du, L.cj);
+                    if (!DELTA) xn += rec[R::RB + (L.isx ? L.r : 0)];
+                    L.dx = L.isx ? xn : 0.0;
                 }
-                const double psel = L.r == 0 ? ps[0] : L.r == 1 ? ps[1] : L.r == 2 ? ps[2] : 0.0;
-                double xn = psel + ltk[L.ksf] * L.dx + ltk[L.kpf] * L.dxp + ltk[L.kuf] * pick(L.du, L.cj);
-                if (!DELTA) xn += rec[R::RB + L.r];
-                L.dx = xn;
             CO_PHASE_END_NS
         }
         // ratio test (max of the negated step) and the three mu sums over the group
@@ -788,13 +795,14 @@ struct Coop {
                 if (!L.act) {
                     const int idx = *reinterpret_cast<const int*>(sm + L.so + O_AST + 1);
                     if (idx < n) {
-                        L.act = true; L.li = idx;
-                        L.first = rs.list == nullptr; L.skipB = !L.first;
+                        L.act = true;
+                        L.first = rs.ctl == nullptr; L.skipB = !L.first;
                         L.gi = rs.list ? rs.list[idx] : idx;
+                        L.li = rs.ctl ? idx : L.gi;               // resumed instances live in compacted records, fresh ones in their own
                         const double* wp = We_inst ? We_inst + i0 + L.gi : tb.We;
                         const size_t wl = We_inst ? (size_t)ldWe : 1;
                         L.We_j = L.isx ? wp[(size_t)L.r * wl] : 0.0;
-                        if (L.r == 0) { if (rs.list) CTL(L) = reinterpret_cast<const LaneCtl*>(rs.ctl)[idx]; else CTL(L).init(true); }
+                        if (L.r == 0) { if (rs.ctl) CTL(L) = reinterpret_cast<const LaneCtl*>(rs.ctl)[idx]; else CTL(L).init(true); }
                     }
                 } else if (L.r == 0) sm[L.so + O_AST] = S::before_B(CTL(L));
             GRP_PHASE_END

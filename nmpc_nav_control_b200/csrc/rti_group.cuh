@@ -164,6 +164,7 @@ struct GrpOut {            // per-instance results of K3 (global, indexed by ins
 // hand-over from the per-sweep kernels (hybrid schedule): the queue holds *n_dev records, record q belongs to
 // instance list[q] of the chunk, is in the middle of an iteration (factorised, predictor not yet run) and
 // continues with the control block ctl[q] (an array of Rti<M>::LaneCtl).  All null = every instance from the cold start.
+// list without ctl (SQP passes): the queue holds *n_dev instances list[q], each from the cold start in its own record.
 struct GrpResume {
     const int* n_dev;
     const int* list;
@@ -1012,14 +1013,15 @@ struct Grp {
                 if (!L.act) {
                     const int idx = *reinterpret_cast<const int*>(sm + L.so + O_RED);
                     if (idx < n) {
-                        L.act = true; L.li = idx;
-                        L.first = rs.list == nullptr; L.skipB = !L.first;
+                        L.act = true;
+                        L.first = rs.ctl == nullptr; L.skipB = !L.first;
                         L.gi = rs.list ? rs.list[idx] : idx;
+                        L.li = rs.ctl ? idx : L.gi;               // resumed instances live in compacted records, fresh ones in their own
                         const double* wp = We_inst ? We_inst + i0 + L.gi : tb.We;
                         const size_t wl = We_inst ? (size_t)ldWe : 1;
                         L.We_c = (L.r < NC && L.cq_x >= 0) ? wp[(size_t)L.cq_x * wl] : 0.0;
                         L.We_xy = L.r == XL ? wp[0] : (L.r == YL ? wp[wl] : 0.0);
-                        if (L.r == 0) { if (rs.list) CTL(L) = reinterpret_cast<const LaneCtl*>(rs.ctl)[idx]; else CTL(L).init(true); }
+                        if (L.r == 0) { if (rs.ctl) CTL(L) = reinterpret_cast<const LaneCtl*>(rs.ctl)[idx]; else CTL(L).init(true); }
                     }
                 } else if (L.r == 0) sm[L.so + O_AST] = S::before_B(CTL(L));
             GRP_PHASE_END

@@ -144,7 +144,7 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
 //   gate: number of lanes still iterating (act[it]); 0 -> the whole grid returns at once.
 //   cnt_out (B kernels): lanes that continue -> act[it+1].
 template <class M, int KIND>
-__global__ void __launch_bounds__(LANES * SW_TILES, (KIND == 5 ? NMPC_FDF_MINB : 8) / SW_TILES)
+__global__ void __launch_bounds__(LANES * SW_TILES, (KIND == Rti<M>::SW_FDF ? NMPC_FDF_MINB : 8) / SW_TILES)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
         double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min,
         int defer_fb)
@@ -188,14 +188,15 @@ template <class M>
 __global__ void __launch_bounds__(LING_BLOCK)
 k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const double* __restrict__ yref, int nyref,
               const double* __restrict__ We_inst, const double* __restrict__ x, const double* __restrict__ u, int ld,
-              Tables tb, IpmOpts o, double* __restrict__ ws)
+              Tables tb, IpmOpts o, double* __restrict__ ws, const int* __restrict__ active)
 {
     using S = Rti<M>;
     using GR = GRec<S::NV>;
     constexpr int HEAD = GR::LHD, TAIL = GR::NREC - GR::MC, ROW = (HEAD + TAIL) | 1;   // odd row stride: conflict-free
     extern __shared__ double lin_sm[];
     const int li = blockIdx.x * LING_BLOCK + threadIdx.x, k = blockIdx.y;
-    if (li < nchunk) {
+    const bool on = li < nchunk && (!active || active[i0 + li] != 0);      // SQP passes: instances that stopped iterating keep their records
+    if (on) {
         const int i = i0 + li;
         double xk[S::NX], uk[S::NU], xk1[S::NX], yr[S::NY], xb[S::NX], We[S::NX];
 #pragma unroll
@@ -225,6 +226,7 @@ k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const
     for (int idx = threadIdx.x; idx < nrow * (HEAD + TAIL); idx += LING_BLOCK) {
         const int r = idx / (HEAD + TAIL), d = idx - r * (HEAD + TAIL);
         const int off = d < HEAD ? d : GR::MC + (d - HEAD);
+        if (active && active[i0 + blockIdx.x * LING_BLOCK + r] == 0) continue;
         ws[(size_t)(blockIdx.x * LING_BLOCK + r) * GR::inst_doubles + (size_t)k * GR::NREC + off] = lin_sm[(size_t)r * ROW + d];
     }
 }
@@ -271,13 +273,15 @@ k_ipm_coop(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldW
 template <class M>
 __global__ void __launch_bounds__(LIN_BLOCK)
 k_step_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __restrict__ x, double* __restrict__ u, int ld,
-         const double* __restrict__ ws, const int* __restrict__ qp_status, int* __restrict__ status)
+         const double* __restrict__ ws, const int* __restrict__ qp_status, int* __restrict__ status,
+         const int* __restrict__ active, unsigned long long* __restrict__ stepn)
 {
     using S = Rti<M>;
     using GR = GRec<S::NV>;
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= nchunk) return;
     const int i = i0 + li, k = blockIdx.y;
+    if (active && active[i] == 0) return;
     const int qs = qp_status[i];
     if (qs != 0 && qs != 1) { if (k == 0) status[i] = NMPC_QP_FAILURE; return; }
     const double* rec = ws + (size_t)li * GR::inst_doubles + (size_t)k * GR::NREC;
@@ -288,7 +292,24 @@ k_step_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __
 #pragma unroll
         for (int c = 0; c < S::NU; c++) uk[c] = u[((size_t)k * S::NU + c) * ld + i];
     }
-    S::template step_stage<GR, 1>(k, rec, xb, xk, uk);
+    if (stepn) {
+        // inf-norm of this stage's step (SQP convergence test): x_0 <- x0bar counts with its distance to the old x_0
+        double xo[S::NX], uo[S::NU];
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) xo[j] = xk[j];
+#pragma unroll
+        for (int c = 0; c < S::NU; c++) uo[c] = k < NSTAGE ? uk[c] : 0.0;
+        S::template step_stage<GR, 1>(k, rec, xb, xk, uk);
+        double nrm = 0.0;
+#pragma unroll
+        for (int j = 0; j < S::NX; j++) nrm = fmax(nrm, fabs(xk[j] - xo[j]));
+        if (k < NSTAGE) {
+#pragma unroll
+            for (int c = 0; c < S::NU; c++) nrm = fmax(nrm, fabs(uk[c] - uo[c]));
+        }
+        if (!(nrm == nrm)) nrm = 1e300;                                  // NaN: never "converged"
+        atomicMax(&stepn[i], (unsigned long long)__double_as_longlong(nrm));   // non-negative doubles order like their bit patterns
+    } else S::template step_stage<GR, 1>(k, rec, xb, xk, uk);
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < S::NX; j++) { x[((size_t)k * S::NX + j) * ld + i] = xk[j]; bad |= (xk[j] != xk[j]); }
@@ -297,6 +318,55 @@ k_step_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, double* __
         for (int c = 0; c < S::NU; c++) u[((size_t)k * S::NU + c) * ld + i] = uk[c];
     }
     if (bad) atomicMax(&status[i], NMPC_NAN_DETECTED);
+}
+
+// ---- BASELINE config 4 (north star kernel (4)): SQP bookkeeping and the warm-start shift ------------------------------
+// per-instance state of an SQP solve: active (still iterating), RTI steps taken, QP iterations summed, step inf-norm
+__global__ void k_sqp_begin(int B, int* __restrict__ active, int* __restrict__ sqp_iter, int* __restrict__ qp_total,
+                            unsigned long long* __restrict__ stepn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    active[i] = 1; sqp_iter[i] = 0; qp_total[i] = 0; stepn[i] = 0ull;
+}
+// queue of one chunk's active instances (order = arrival; an instance's result does not depend on its slot)
+__global__ void k_sqp_list(int i0, int nchunk, const int* __restrict__ active, int* __restrict__ count, int* __restrict__ list)
+{
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = li < nchunk && active[i0 + li] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (on) list[base + __popc(m & ((1u << lane) - 1u))] = li;
+}
+// after an RTI pass: count it, stop the instances that converged (step <= tol), failed or reached max_iter
+__global__ void k_sqp_update(int B, int max_iter, double tol, int* __restrict__ active, const int* __restrict__ status,
+                             const int* __restrict__ qp_iter, int* __restrict__ sqp_iter, int* __restrict__ qp_total,
+                             unsigned long long* __restrict__ stepn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B || active[i] == 0) return;
+    const int it = sqp_iter[i] + 1;
+    sqp_iter[i] = it; qp_total[i] += qp_iter[i];
+    const double nrm = __longlong_as_double((long long)stepn[i]);
+    stepn[i] = 0ull;
+    if (status[i] != 0 || nrm <= tol || it >= max_iter) active[i] = 0;
+}
+// warm-start shift (scripts/test_scripts/casadi_sim_diff.py:104-106 warm-starts from the previous
+// solution): row r of the stage-major iterate takes the value one stage later, the last stage is kept.
+// grid: (ceil(B / 128), rows) with rows = nx for x (nstages = N + 1) or nu for u (nstages = N)
+__global__ void k_shift(int B, int ld, int rows, int nstages, double* __restrict__ a, const int* __restrict__ mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (i >= B || (mask && mask[i] == 0)) return;
+    double nxt = a[((size_t)1 * rows + r) * ld + i];
+    for (int k = 0; k + 1 < nstages; k++) {
+        a[((size_t)k * rows + r) * ld + i] = nxt;
+        if (k + 2 < nstages) nxt = a[((size_t)(k + 2) * rows + r) * ld + i];
+    }
 }
 
 // ---- hybrid schedule: hand-over of the instances the per-sweep kernels did not finish ----------------------
@@ -633,7 +703,8 @@ struct nmpc_solver {
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
     int k3_impl = 1;             // lane-group kernel: 0 first mapping (rti_group.cuh), 1 lane-cooperative mapping (rti_coop.cuh)
-    int hyb_kmax = 12; double hyb_frac = 0.6;   // hand over once fewer than 60 % of the chunk iterate (sweep in profiles/README_r01_notes.txt)
+    int hyb_kmax = 12; double hyb_frac = 0.75;  // hand over once fewer than 75 % of the chunk iterate: a lockstep launch costs the same at any
+                                 // active fraction (17.5 k instance-iterations / ms when full), the lane-cooperative kernel sustains 12.7 k
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_G = 0, grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
@@ -648,6 +719,8 @@ struct nmpc_solver {
     size_t off_W, off_We, off_lbx, off_ubx, off_lbu, off_ubu, off_p, off_lti, off_thr, off_stg, tab_doubles;
     int t_w = 0, trow = 0;
     bool tab_dirty = true, p_dirty = true;
+    double* h_tab = nullptr;      // pinned mirror of the uploaded part of d_tab
+    cudaEvent_t ev_tab = nullptr; // the last upload has left the mirror
     double *d_x = nullptr, *d_u = nullptr;       // persisted iterate, SoA, ld = cap
     double *d_ws = nullptr;                      // tile workspace for one chunk
     double *d_ctl_d = nullptr;                   // K3 control block of one chunk
@@ -660,6 +733,9 @@ struct nmpc_solver {
     int *d_status = nullptr, *d_iter = nullptr;
     double *d_stats = nullptr;                   // [8][cap] statistics of the last host call
     int last_host_B = 0;
+    int *d_sqp_active = nullptr, *d_sqp_iter = nullptr, *d_sqp_qp = nullptr;   // SQP solve: per-instance bookkeeping [cap]
+    unsigned long long* d_sqp_stepn = nullptr;
+    double *d_roll_refs = nullptr, *d_roll_cmd = nullptr;                      // rollout engine: reference poses, commands
     double *d_vref = nullptr;                    // controller glue: carried reference states [nv][cap]
     double *d_cin = nullptr; int *d_cnref = nullptr;   // controller glue, host call: pose | vel | steer | cmd | refs (SoA, ld = B)
     cudaStream_t own_stream = nullptr;
@@ -796,10 +872,14 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
     cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
     cudaFree(s->d_status); cudaFree(s->d_iter); cudaFree(s->d_stats);
+    cudaFree(s->d_sqp_active); cudaFree(s->d_sqp_iter); cudaFree(s->d_sqp_qp); cudaFree(s->d_sqp_stepn);
+    cudaFree(s->d_roll_refs); cudaFree(s->d_roll_cmd);
     for (auto e : s->ev) cudaEventDestroy(e);
     if (s->ev_total[0]) cudaEventDestroy(s->ev_total[0]);
     if (s->ev_total[1]) cudaEventDestroy(s->ev_total[1]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->ev_tab) cudaEventDestroy(s->ev_tab);
+    if (s->h_tab) cudaFreeHost(s->h_tab);
     delete s;
     return 0;
 }
@@ -867,7 +947,13 @@ static int launch_lti(nmpc_solver* s, cudaStream_t st)
 static int upload_tables(nmpc_solver* s, cudaStream_t st)
 {
     if (!s->tab_dirty) return 0;
-    std::vector<double> h(s->off_lti);
+    // one asynchronous copy of the packed tables from a pinned mirror, on the stream of the kernels that read them;
+    // the host only waits if the previous upload has not left the mirror yet
+    if (!s->h_tab) {
+        CK(cudaMallocHost(&s->h_tab, s->off_lti * sizeof(double)));
+        CK(cudaEventCreateWithFlags(&s->ev_tab, cudaEventDisableTiming));
+    } else CK(cudaEventSynchronize(s->ev_tab));
+    double* h = s->h_tab;
     memcpy(&h[s->off_W], s->W.data(), s->W.size() * 8);
     memcpy(&h[s->off_We], s->We.data(), s->We.size() * 8);
     memcpy(&h[s->off_lbx], s->lbx.data(), s->lbx.size() * 8);
@@ -875,9 +961,8 @@ static int upload_tables(nmpc_solver* s, cudaStream_t st)
     memcpy(&h[s->off_lbu], s->lbu.data(), s->lbu.size() * 8);
     memcpy(&h[s->off_ubu], s->ubu.data(), s->ubu.size() * 8);
     memcpy(&h[s->off_p], s->p.data(), s->p.size() * 8);
-    // synchronous copy from a pageable temporary: tables change rarely (set-up, or W_e per tick at batch 1)
-    CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpy(s->d_tab, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(s->d_tab, h, s->off_lti * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(s->ev_tab, st));
     if (s->p_dirty) {
         int rc = s->model == 0 ? launch_lti<DiffModel>(s, st) : s->model == 1 ? launch_lti<Omni4Model>(s, st) : launch_lti<TricModel>(s, st);
         if (rc) return rc;
@@ -962,7 +1047,7 @@ static int launch_group_any(nmpc_solver* s, int i0, int n, const Tables& tb, con
     using S = Rti<M>;
     const int G = s->grp_G;
     if (s->k3_impl == 1)       // lane-cooperative mapping (rti_coop.cuh): G = 4 nv lanes per instance
-        return launch_group_k<Coop<M, 4 * S::NV>>(s, k_ipm_coop<M, 4 * S::NV, NMPC_COOP_MINB>, i0, n, tb, d_We, ldWe, o, out, rs, st);
+        return launch_group_k<Coop<M, 4 * S::NV>>(s, k_ipm_coop<M, 4 * S::NV, (S::NV == 2 ? NMPC_COOP_MINB : 2)>, i0, n, tb, d_We, ldWe, o, out, rs, st);
     if constexpr (S::NV == 2) {
         if (G == 8) return launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
         if (G == 16) return launch_group<M, 16, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
@@ -1050,9 +1135,12 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
 }
 
 
+// d_active / d_stepn (SQP passes, else null): only the instances with a non-zero flag are linearised, solved (through a
+// compacted queue) and stepped; the inf-norm of their step is accumulated into d_stepn
 template <class M>
 static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
-                              double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st)
+                              double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st,
+                              const int* d_active = nullptr, unsigned long long* d_stepn = nullptr)
 {
     using S = Rti<M>;
     using GR = GRec<S::NV>;
@@ -1062,8 +1150,10 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
     int rc = ensure_events(s, nchunks);
     if (rc) return rc;
     s->last_chunks = nchunks; s->last_launches = 0;
-    k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
-    s->last_launches++;
+    if (!d_active) {
+        k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
+        s->last_launches++;
+    }
     const size_t sm_lin = (size_t)LING_BLOCK * ((GR::LHD + GR::NREC - GR::MC) | 1) * sizeof(double);
     bool& attr_set = s->lin_attr_set;
     if (!attr_set) {
@@ -1077,12 +1167,20 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
         cudaEvent_t* ev = &s->ev[(size_t)c * 4];
         CK(cudaEventRecord(ev[0], st));
         dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1), g0((n + LING_BLOCK - 1) / LING_BLOCK, NSTAGE + 1);
-        k_linearize_g<M><<<g0, LING_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, o, s->d_ws_g);
+        k_linearize_g<M><<<g0, LING_BLOCK, sm_lin, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, o, s->d_ws_g, d_active);
         CK(cudaEventRecord(ev[1], st));
-        rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nullptr, nullptr, nullptr}, st);
+        GrpResume rs{nullptr, nullptr, nullptr};
+        if (d_active) {
+            int* cnt = s->d_cnt + s->cnt_cap - 2;
+            CK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+            k_sqp_list<<<(n + 255) / 256, 256, 0, st>>>(i0, n, d_active, cnt, s->d_list);
+            rs = GrpResume{cnt, s->d_list, nullptr};
+            s->last_launches++;
+        }
+        rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, rs, st);
         if (rc) return rc;
         CK(cudaEventRecord(ev[2], st));
-        k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws_g, s->d_qp_status, d_status);
+        k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws_g, s->d_qp_status, d_status, d_active, d_stepn);
         CK(cudaEventRecord(ev[3], st));
         s->last_launches += 3;
     }
@@ -1119,6 +1217,85 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
         default: rc = solve_device_t<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
     }
     if (rc) return rc;
+    CK(cudaEventRecord(s->ev_total[1], st));
+    return 0;
+}
+
+// ---- BASELINE config 4: warm-start shift and SQP to convergence (declared in include/nmpc_b200.h) ------------------
+extern "C" int nmpc_shift_device(nmpc_solver* s, int B, double* d_x, double* d_u, int ldxu, const int* d_mask, void* stream)
+{
+    if (!s) return set_err(NMPC_E_ARG, "nmpc_shift_device: null solver");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_shift_device: B < 1");
+    if ((d_x == nullptr) != (d_u == nullptr)) return set_err(NMPC_E_ARG, "nmpc_shift_device: pass both d_x and d_u or neither");
+    if (!d_x) { if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_shift_device: batch exceeds capacity"); d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
+    if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_shift_device: leading dimension < B");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_shift<<<dim3((B + 127) / 128, s->mi.nx), 128, 0, st>>>(B, ldxu, s->mi.nx, NSTAGE + 1, d_x, d_mask);
+    k_shift<<<dim3((B + 127) / 128, s->mi.nu), 128, 0, st>>>(B, ldxu, s->mi.nu, NSTAGE, d_u, d_mask);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_staging(nmpc_solver* s);
+static int ensure_sqp(nmpc_solver* s)
+{
+    if (s->d_sqp_active) return 0;
+    CK(cudaMalloc(&s->d_sqp_active, (size_t)s->cap * sizeof(int)));
+    CK(cudaMalloc(&s->d_sqp_iter, (size_t)s->cap * sizeof(int)));
+    CK(cudaMalloc(&s->d_sqp_qp, (size_t)s->cap * sizeof(int)));
+    CK(cudaMalloc(&s->d_sqp_stepn, (size_t)s->cap * sizeof(unsigned long long)));
+    return 0;
+}
+
+static int group_pass(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
+                      double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, cudaStream_t st, const int* d_active,
+                      unsigned long long* d_stepn)
+{
+    switch (s->model) {
+        case 0: return solve_device_group<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, d_status, d_qp_iter, nullptr, st, d_active, d_stepn);
+        case 1: return solve_device_group<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, d_status, d_qp_iter, nullptr, st, d_active, d_stepn);
+        default: return solve_device_group<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, d_status, d_qp_iter, nullptr, st, d_active, d_stepn);
+    }
+}
+
+extern "C" int nmpc_sqp_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref,
+                                     const double* d_We, double* d_x, double* d_u, int ldxu, int max_iter, double tol,
+                                     int* d_status, int* d_sqp_iter, int* d_qp_iter, void* stream)
+{
+    if (!s || !d_x0bar || !d_yref || !d_status) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: null argument");
+    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: B < 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_sqp_solve_device: batch exceeds capacity");
+    if (max_iter < 1 || max_iter > 1000) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: max_iter must be 1..1000");
+    if (!(tol >= 0.0)) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: tol must be >= 0");
+    const int ny = s->mi.nx + s->mi.nu;
+    if (nyref != 3 && nyref != ny) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: nyref must be 3 or ny");
+    if ((d_x == nullptr) != (d_u == nullptr)) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: pass both d_x and d_u or neither");
+    if (!s->d_ws_g) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: needs the lane-group workspace (NMPC_K3=sweep excludes it)");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_tables(s, st); if (rc) return rc;
+    rc = ensure_sqp(s); if (rc) return rc;
+    rc = ensure_staging(s); if (rc) return rc;
+    if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
+    if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_sqp_solve_device: leading dimension < B");
+    CK(cudaEventRecord(s->ev_total[0], st));
+    const int nb = (B + 255) / 256;
+    k_sqp_begin<<<nb, 256, 0, st>>>(B, s->d_sqp_active, s->d_sqp_iter, s->d_sqp_qp, s->d_sqp_stepn);
+    k_fill_int<<<nb, 256, 0, st>>>(B, d_status, 0);
+    int launches = 2;
+    // every pass is enqueued; a pass only touches the instances still iterating (their queue is built on the device),
+    // so the passes after the last instance stopped cost a handful of empty launches
+    for (int it = 0; it < max_iter; it++) {
+        rc = group_pass(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, s->d_iter, st, s->d_sqp_active, s->d_sqp_stepn);
+        if (rc) return rc;
+        k_sqp_update<<<nb, 256, 0, st>>>(B, max_iter, tol, s->d_sqp_active, d_status, s->d_iter, s->d_sqp_iter, s->d_sqp_qp, s->d_sqp_stepn);
+        launches += s->last_launches + 1;
+    }
+    if (d_sqp_iter) CK(cudaMemcpyAsync(d_sqp_iter, s->d_sqp_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (d_qp_iter) CK(cudaMemcpyAsync(d_qp_iter, s->d_sqp_qp, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    s->last_launches = launches;
     CK(cudaEventRecord(s->ev_total[1], st));
     return 0;
 }
@@ -1264,11 +1441,11 @@ extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, c
 }
 
 // ---- batched controller tick (declared in include/nmpc_b200.h) ------------------
-static int ensure_ctrl(nmpc_solver* s)
+static int ensure_ctrl(nmpc_solver* s, cudaStream_t st)
 {
     if (s->d_vref) return 0;
     CK(cudaMalloc(&s->d_vref, (size_t)s->cap * s->mi.nv * sizeof(double)));
-    CK(cudaMemset(s->d_vref, 0, (size_t)s->cap * s->mi.nv * sizeof(double)));
+    CK(cudaMemsetAsync(s->d_vref, 0, (size_t)s->cap * s->mi.nv * sizeof(double), st));   // ordered before the first tick on st
     return 0;
 }
 
@@ -1276,9 +1453,10 @@ extern "C" int nmpc_ctrl_reset(nmpc_solver* s, void* stream)
 {
     if (!s) return set_err(NMPC_E_ARG, "null solver");
     CK(cudaSetDevice(s->device));
-    int rc = ensure_ctrl(s);
+    int rc = ensure_ctrl(s, (cudaStream_t)stream);
     if (rc) return rc;
     CK(cudaMemsetAsync(s->d_vref, 0, (size_t)s->cap * s->mi.nv * sizeof(double), (cudaStream_t)stream));
+    if (s->d_roll_cmd) CK(cudaMemsetAsync(s->d_roll_cmd, 0, (size_t)s->cap * 3 * sizeof(double), (cudaStream_t)stream));   // the rollout engine's commands
     return 0;
 }
 
@@ -1286,28 +1464,25 @@ extern "C" int nmpc_ctrl_state_device(nmpc_solver* s, double** d_vref, int* lead
 {
     if (!s) return set_err(NMPC_E_ARG, "null solver");
     CK(cudaSetDevice(s->device));
-    int rc = ensure_ctrl(s);
+    const bool fresh = s->d_vref == nullptr;
+    int rc = ensure_ctrl(s, s->own_stream);
     if (rc) return rc;
+    if (fresh) CK(cudaStreamSynchronize(s->own_stream));      // the caller may touch the buffer on any stream
     if (d_vref) *d_vref = s->d_vref;
     if (leading_dim) *leading_dim = s->cap;
     return 0;
 }
 
-extern "C" int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
-                                     const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd,
-                                     int* d_status, int* d_qp_iter, void* stream)
+// one tick for B robots on `st`: pre-processing kernel, RTI step (sqp_max_iter <= 1, the reference's behaviour) or SQP to
+// convergence on the persisted iterate, post-processing kernel
+static int ctrl_tick_core(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                          const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd, int* d_status,
+                          int* d_qp_iter, int sqp_max_iter, double sqp_tol, void* stream)
 {
-    if (!s || !d_pose || !d_vel || !d_refs || !d_cmd) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: null argument");
-    if (B < 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: B < 1");
-    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_ctrl_tick_device: batch exceeds capacity");
-    if (nref_max < 1) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: nref_max < 1 (run() needs at least one reference pose)");
-    if (s->model == NMPC_MODEL_TRIC && !d_steer) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: tric needs the measured steering angle");
-    if (!(dt > 0.0)) return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_device: dt must be positive");
-    CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_staging(s);
     if (rc) return rc;
-    rc = ensure_ctrl(s);
+    rc = ensure_ctrl(s, st);
     if (rc) return rc;
     rc = upload_tables(s, st);
     if (rc) return rc;
@@ -1324,7 +1499,11 @@ extern "C" int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose
         default: k_ctrl_pre<TricModel><<<nb, 128, 0, st>>>(B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, s->d_vref, s->cap, p, W0, Wt, s->d_x0bar, s->d_yref, We); break;
     }
     CK(cudaGetLastError());
-    rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, 3, We, nullptr, nullptr, 0, d_status, d_qp_iter, nullptr, stream);
+    if (sqp_max_iter <= 1)
+        rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, 3, We, nullptr, nullptr, 0, d_status, d_qp_iter, nullptr, stream);
+    else
+        rc = nmpc_sqp_solve_device(s, B, s->d_x0bar, s->d_yref, 3, We, nullptr, nullptr, 0, sqp_max_iter, sqp_tol, d_status, nullptr,
+                                   d_qp_iter, stream);
     if (rc) return rc;
     switch (s->model) {
         case 0: k_ctrl_post<DiffModel><<<nb, 128, 0, st>>>(B, d_status, s->d_x0bar, s->d_u, s->cap, dt, p, s->d_vref, s->cap, d_cmd); break;
@@ -1334,6 +1513,42 @@ extern "C" int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose
     CK(cudaGetLastError());
     s->last_launches += 2;
     return 0;
+}
+
+static int ctrl_tick_check(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                           const double* d_refs, int nref_max, double dt, double* d_cmd, const char* who)
+{
+    static thread_local char msg[160];
+    auto bad = [&](int code, const char* what) { snprintf(msg, sizeof(msg), "%s: %s", who, what); return set_err(code, msg); };
+    if (!s || !d_pose || !d_vel || !d_refs || !d_cmd) return bad(NMPC_E_ARG, "null argument");
+    if (B < 1) return bad(NMPC_E_ARG, "B < 1");
+    if (B > s->cap) return bad(NMPC_E_CAPACITY, "batch exceeds capacity");
+    if (nref_max < 1) return bad(NMPC_E_ARG, "nref_max < 1 (run() needs at least one reference pose)");
+    if (s->model == NMPC_MODEL_TRIC && !d_steer) return bad(NMPC_E_ARG, "tric needs the measured steering angle");
+    if (!(dt > 0.0)) return bad(NMPC_E_ARG, "dt must be positive");
+    return 0;
+}
+
+extern "C" int nmpc_ctrl_tick_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                                     const double* d_refs, const int* d_nref, int nref_max, double dt, double* d_cmd,
+                                     int* d_status, int* d_qp_iter, void* stream)
+{
+    int rc = ctrl_tick_check(s, B, d_pose, d_vel, d_steer, d_refs, nref_max, dt, d_cmd, "nmpc_ctrl_tick_device");
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    return ctrl_tick_core(s, B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, dt, d_cmd, d_status, d_qp_iter, 1, 0.0, stream);
+}
+
+extern "C" int nmpc_ctrl_tick_sqp_device(nmpc_solver* s, int B, const double* d_pose, const double* d_vel, const double* d_steer,
+                                         const double* d_refs, const int* d_nref, int nref_max, double dt, int sqp_max_iter,
+                                         double sqp_tol, double* d_cmd, int* d_status, int* d_qp_iter, void* stream)
+{
+    int rc = ctrl_tick_check(s, B, d_pose, d_vel, d_steer, d_refs, nref_max, dt, d_cmd, "nmpc_ctrl_tick_sqp_device");
+    if (rc) return rc;
+    if (sqp_max_iter < 1 || sqp_max_iter > 1000 || !(sqp_tol >= 0.0))
+        return set_err(NMPC_E_ARG, "nmpc_ctrl_tick_sqp_device: sqp_max_iter must be 1..1000 and sqp_tol >= 0");
+    CK(cudaSetDevice(s->device));
+    return ctrl_tick_core(s, B, d_pose, d_vel, d_steer, d_refs, d_nref, nref_max, dt, d_cmd, d_status, d_qp_iter, sqp_max_iter, sqp_tol, stream);
 }
 
 // host-buffer form of the tick: instance-major arrays, copied and transposed on the device like nmpc_rti_solve_host
@@ -1430,6 +1645,65 @@ extern "C" int nmpc_path_nearest_device(int device, int B, const double* d_segme
     CK(cudaSetDevice(device));
     k_path_nearest<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(B, d_segments, d_path_offsets, n_paths, d_path_id, d_pose, back, ahead, d_u);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- the closed-loop rollout engine ------------------------------------------------------------------
+__global__ void k_count_nonzero(int B, const int* __restrict__ a, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = __ballot_sync(0xffffffffu, i < B && a[i] != 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
+extern "C" int nmpc_rollout_device(nmpc_solver* s, int B, int ticks, const nmpc_rollout_opts* o, const double* d_segments,
+                                   const int* d_path_offsets, int n_paths, const int* d_path_id, double* d_u, double* d_xplant,
+                                   double* d_pose, double* d_vel, double* d_steer, const double* d_noise, double* d_traj,
+                                   double* d_cmds, int* d_nfail, void* stream)
+{
+    if (!s || !o || !d_segments || !d_path_offsets || !d_u || !d_xplant || !d_pose || !d_vel)
+        return set_err(NMPC_E_ARG, "nmpc_rollout_device: null argument");
+    if (B < 1 || ticks < 1 || n_paths < 1) return set_err(NMPC_E_ARG, "nmpc_rollout_device: B, ticks and n_paths must be >= 1");
+    if (B > s->cap) return set_err(NMPC_E_CAPACITY, "nmpc_rollout_device: batch exceeds capacity");
+    if (!(o->dt > 0.0) || !(o->back >= 0.0) || !(o->ahead >= 0.0)) return set_err(NMPC_E_ARG, "nmpc_rollout_device: dt > 0 and a non-negative search window are required");
+    if (o->sqp_max_iter < 1 || o->sqp_max_iter > 1000 || !(o->sqp_tol >= 0.0)) return set_err(NMPC_E_ARG, "nmpc_rollout_device: sqp_max_iter must be 1..1000 and sqp_tol >= 0");
+    if (s->model == NMPC_MODEL_TRIC && !d_steer) return set_err(NMPC_E_ARG, "nmpc_rollout_device: tric needs the steering-angle buffer");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!s->d_roll_refs) {
+        CK(cudaMalloc(&s->d_roll_refs, (size_t)s->cap * 3 * (NSTAGE + 1) * sizeof(double)));
+        CK(cudaMalloc(&s->d_roll_cmd, (size_t)s->cap * 3 * sizeof(double)));
+        CK(cudaMemsetAsync(s->d_roll_cmd, 0, (size_t)s->cap * 3 * sizeof(double), st));
+    }
+    const size_t row3 = (size_t)3 * B * sizeof(double);
+    if (d_traj) CK(cudaMemcpyAsync(d_traj, d_pose, row3, cudaMemcpyDeviceToDevice, st));
+    if (d_nfail) CK(cudaMemsetAsync(d_nfail, 0, (size_t)ticks * sizeof(int), st));
+    int launches = 0;
+    for (int t = 0; t < ticks; t++) {
+        // the order of NMPCNavControlROS::processFollowPath (NMPCNavControlROS.cpp:648-698): nearest point, N+1 reference
+        // poses, run(); then the nominal plant (scripts/test_scripts/acados_sim_diff.py:136-160) and the optional shift
+        int rc = nmpc_path_nearest_device(s->device, B, d_segments, d_path_offsets, n_paths, d_path_id, d_pose, o->back, o->ahead, d_u, stream);
+        if (rc) return rc;
+        rc = nmpc_path_discretize_device(s->device, B, d_segments, d_path_offsets, n_paths, d_path_id, d_u, o->dt, NSTAGE + 1,
+                                         o->is_holonomic, s->d_roll_refs, stream);
+        if (rc) return rc;
+        rc = ctrl_tick_core(s, B, d_pose, d_vel, d_steer, s->d_roll_refs, nullptr, NSTAGE + 1, o->dt, s->d_roll_cmd, s->d_status, s->d_iter,
+                            o->sqp_max_iter, o->sqp_tol, stream);
+        if (rc) return rc;
+        launches += s->last_launches + 3;
+        if (d_cmds) CK(cudaMemcpyAsync(d_cmds + (size_t)t * 3 * B, s->d_roll_cmd, row3, cudaMemcpyDeviceToDevice, st));
+        if (d_nfail) k_count_nonzero<<<(B + 255) / 256, 256, 0, st>>>(B, s->d_status, d_nfail + t);
+        rc = nmpc_plant_step_device(s, B, o->dt, d_noise ? d_noise + (size_t)t * s->mi.nu * B : nullptr, d_xplant, d_pose, d_vel, d_steer, stream);
+        if (rc) return rc;
+        if (d_traj) CK(cudaMemcpyAsync(d_traj + (size_t)(t + 1) * 3 * B, d_pose, row3, cudaMemcpyDeviceToDevice, st));
+        if (o->shift) {
+            rc = nmpc_shift_device(s, B, nullptr, nullptr, 0, nullptr, stream);
+            if (rc) return rc;
+            launches += 2;
+        }
+    }
+    CK(cudaGetLastError());
+    s->last_launches = launches;
     return 0;
 }
 

@@ -63,6 +63,29 @@ class ClosedLoopRollout:
                    "nmpc_plant_step_device")
         return self.out
 
+    def run_engine(self, ticks: int, noise: torch.Tensor | None = None, sqp_max_iter: int = 1, sqp_tol: float = 0.0,
+                   shift: bool = False):
+        """`ticks` closed-loop ticks through ONE call of the C ABI (`nmpc_rollout_device`): the library enqueues nearest
+        point -> reference poses -> controller tick (RTI, or SQP to convergence) -> plant step -> optional warm-start
+        shift for every tick on torch's current stream; no Python (and no host synchronisation) between ticks.
+        noise [ticks,nu,B] or None.  Returns dict(pose [ticks+1,3,B], cmd [ticks,3,B], failed [ticks] int32)."""
+        f64 = dict(dtype=torch.float64, device=self.tdev)
+        B = self.B
+        traj = torch.empty(ticks + 1, 3, B, **f64); cmds = torch.empty(ticks, 3, B, **f64)
+        failed = torch.zeros(ticks, dtype=torch.int32, device=self.tdev)
+        if noise is not None:
+            assert noise.is_cuda and noise.is_contiguous() and noise.shape == (ticks, self.spec.nu, B)
+        o = _lib.RolloutOpts(dt=self.ctl.dt, back=self.back, ahead=self.ahead, sqp_tol=float(sqp_tol),
+                             is_holonomic=int(self.disc.is_holonomic), sqp_max_iter=int(sqp_max_iter), shift=int(bool(shift)))
+        p = self.paths
+        st = C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+        vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.nmpc_rollout_device(self.ctl.solver._h, B, int(ticks), C.byref(o), vp(p.segments), vp(p.offsets), p.n_paths,
+                                                vp(self.path_id), vp(self.u), vp(self.x), vp(self.pose), vp(self.vel),
+                                                vp(self.steer) if self.spec.name == "tric" else None, vp(noise), vp(traj), vp(cmds),
+                                                vp(failed), st), "nmpc_rollout_device")
+        return dict(pose=traj, cmd=cmds, failed=failed)
+
     def run(self, ticks: int, noise: torch.Tensor | None = None):
         """`ticks` closed-loop ticks; noise [ticks,nu,B] or None.  Returns dict(pose [ticks+1,3,B], cmd [ticks,3,B],
         failed [ticks] = robots with a non-zero solver status per tick), CUDA tensors; asynchronous."""

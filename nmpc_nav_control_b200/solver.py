@@ -136,13 +136,61 @@ class BatchedRtiSolver:
             "nmpc_rti_solve_device")
         return out
 
+    # ---- BASELINE config 4: SQP to convergence and the warm-start shift ---------------------------
+    def sqp_solve_device(self, x0bar: torch.Tensor, yref: torch.Tensor, max_iter: int, tol: float, We: torch.Tensor | None = None,
+                         x: torch.Tensor | None = None, u: torch.Tensor | None = None, out: dict | None = None,
+                         stream: torch.cuda.Stream | None = None):
+        """per instance: RTI steps until the inf-norm of the step is <= tol (or max_iter); arguments as solve_device.
+        Returns dict(status, sqp_iter, qp_iter) of CUDA tensors (qp_iter summed over the steps); asynchronous."""
+        s = self.spec
+        B = x0bar.shape[1]
+        nyref = yref.shape[1]
+        for t in (x0bar, yref, We, x, u):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        assert x0bar.shape == (s.nx, B) and yref.shape == (s.n + 1, nyref, B)
+        if out is None:
+            out = {k: torch.empty(B, dtype=torch.int32, device=self.tdev) for k in ("status", "sqp_iter", "qp_iter")}
+        ld = 0
+        if x is not None:
+            assert x.shape == (s.n + 1, s.nx, B) and u.shape == (s.n, s.nu, B)
+            ld = B
+        st = stream if stream is not None else torch.cuda.current_stream(self.tdev)
+        _lib.check(self.lib.nmpc_sqp_solve_device(
+            self._h, B, _ptr(x0bar), _ptr(yref), nyref, _ptr(We), _ptr(x), _ptr(u), ld, int(max_iter), C.c_double(tol),
+            _ptr(out["status"]), _ptr(out["sqp_iter"]), _ptr(out["qp_iter"]), C.c_void_p(st.cuda_stream)), "nmpc_sqp_solve_device")
+        return out
+
+    def shift(self, B: int, x: torch.Tensor | None = None, u: torch.Tensor | None = None, mask: torch.Tensor | None = None,
+              stream: torch.cuda.Stream | None = None):
+        """x_k <- x_{k+1}, u_k <- u_{k+1}, last stage kept (SURVEY.md Appendix D.4); x/u None = the persisted iterate;
+        mask [B] int32 or None"""
+        ld = 0
+        if x is not None:
+            assert x.is_cuda and u.is_cuda and x.is_contiguous() and u.is_contiguous()
+            ld = x.shape[2]
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype == torch.int32 and mask.shape == (B,)
+        st = stream if stream is not None else torch.cuda.current_stream(self.tdev)
+        _lib.check(self.lib.nmpc_shift_device(self._h, B, _ptr(x), _ptr(u), ld, _ptr(mask), C.c_void_p(st.cuda_stream)),
+                   "nmpc_shift_device")
+
     # ---- solve: host buffers, instance-major (the controller-facing call) --------------------
     def solve_host(self, x0bar, yref, We=None, out: dict | None = None):
         """x0bar [B,nx], yref [B,N+1,nyref], We [B,nx] host arrays (numpy or pinned torch).
         Returns dict(u0 [B,nu], x1 [B,nx], status [B], qp_iter [B]) as numpy arrays; synchronous."""
         s = self.spec
+        x0bar = np.ascontiguousarray(x0bar, dtype=np.float64); yref = np.ascontiguousarray(yref, dtype=np.float64)
+        if x0bar.ndim != 2 or x0bar.shape[1] != s.nx:
+            raise ValueError(f"x0bar must be [B, {s.nx}], got {x0bar.shape}")
         B = x0bar.shape[0]
+        if yref.ndim != 3 or yref.shape[:2] != (B, s.n + 1) or yref.shape[2] not in (3, s.ny):
+            raise ValueError(f"yref must be [B, {s.n + 1}, 3 or {s.ny}], got {yref.shape}")
         nyref = yref.shape[2]
+        if We is not None:
+            We = np.ascontiguousarray(We, dtype=np.float64)
+            if We.shape != (B, s.nx):
+                raise ValueError(f"We must be [B, {s.nx}], got {We.shape}")
         if out is None:
             out = dict(u0=np.empty((B, s.nu)), x1=np.empty((B, s.nx)),
                        status=np.empty(B, dtype=np.int32), qp_iter=np.empty(B, dtype=np.int32))

@@ -92,14 +92,31 @@ class OracleController:
             cmd = (new_ref[0], new_ref[1], 0.0)
         return cmd, new_ref
 
-    def run(self, pose, vel, steer, refs):
+    def run(self, pose, vel, steer, refs, sqp_max_iter=1, sqp_tol=0.0):
+        """sqp_max_iter = 1: the reference's single RTI step per tick.  > 1 (BASELINE config 4, not a reference behaviour):
+        RTI steps from the current iterate until the inf-norm of the step is <= sqp_tol or sqp_max_iter steps were taken;
+        returns the QP iterations summed over the steps and keeps the number of steps in self.sqp_steps"""
         s = self.spec
         x0, yref, We = self.pre(pose, vel, steer, refs)
-        r = self.o.rti(x0, yref, self.x, self.u, We=We)
-        assert r["status"] == 0                          # processAcadosStatus throws, NMPCNavControl.cpp:15-24
-        self.x, self.u = r["x"], r["u"]
+        qp_total = 0
+        self.sqp_steps = 0
+        for _ in range(max(1, sqp_max_iter)):
+            r = self.o.rti(x0, yref, self.x, self.u, We=We)
+            assert r["status"] == 0                      # processAcadosStatus throws, NMPCNavControl.cpp:15-24
+            step = max(np.abs(r["x"] - self.x).max(), np.abs(r["u"] - self.u).max())
+            self.x, self.u = r["x"], r["u"]
+            qp_total += r["qp_iter"]
+            self.sqp_steps += 1
+            if sqp_max_iter <= 1 or step <= sqp_tol:
+                break
+        r = dict(qp_iter=qp_total)
         cmd, new_ref = self.post(x0, self.u[0])
         nv = s.nv
         self.x0 = self.x[1].copy()                       # Diff.cpp:168-172
         self.x0[3 + nv:3 + 2 * nv] = new_ref
         return cmd, r["qp_iter"]
+
+    def shift(self):
+        """warm-start shift of the iterate: stage k takes stage k+1, the last stage is kept"""
+        self.x[:-1] = self.x[1:].copy()
+        self.u[:-1] = self.u[1:].copy()

@@ -61,15 +61,18 @@ class OracleRollout:
         self.u, self.back, self.ahead, self.hol = float(u0), back, ahead, holonomic
         self.p = np.array(self.spec.p, dtype=np.float64)
 
-    def step(self, noise=None):
+    def step(self, noise=None, sqp_max_iter=1, sqp_tol=0.0, shift=False):
+        """one tick; sqp_max_iter > 1 / shift: SQP to convergence and the warm-start shift of nmpc_rollout_device"""
         s = self.spec
         self.u = nearest_u(self.seg, self.u, self.pose[0], self.pose[1], self.back, self.ahead)
         refs = pathdisc.get_next_n_poses(self.seg, self.u, s.dt, s.n + 1, self.hol)
-        cmd, qi = self.c.run(self.pose, self.vel, self.steer, [tuple(r) for r in refs])
+        cmd, qi = self.c.run(self.pose, self.vel, self.steer, [tuple(r) for r in refs], sqp_max_iter, sqp_tol)
         u0 = self.c.u[0] + (0.0 if noise is None else np.asarray(noise))
         self.x, _ = self.c.o.discrete_map(self.x, u0, self.p, s.dt)
         self.pose, vel, self.steer = measurements(self.name, s, self.x)
         if vel[2] is None:
             vel = (vel[0], 0.0, 0.0)          # run() does not read w for tric (Tric.cpp:96-98)
         self.vel = vel
+        if shift:
+            self.c.shift()
         return cmd, qi

@@ -96,3 +96,22 @@ def test_cpp_example_compiles_links_and_fails_loudly_without_a_device(tmp_path):
     if not torch.cuda.is_available():
         p = subprocess.run([exe, "8"], capture_output=True, text=True, timeout=120)
         assert p.returncode == 2 and "no CPU fallback" in p.stderr, (p.returncode, p.stderr)
+
+
+def test_cpp_rollout_example_compiles_and_links(tmp_path):
+    """examples/fleet_rollout.cpp: BASELINE config 4 (tric, SQP + warm-start shift, closed loop) through ONE call of
+    nmpc_rollout_device from plain C++; without a CUDA device it exits 2 with the library's message"""
+    from nmpc_nav_control_b200 import build
+    build.build_core()
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA runtime headers not found")
+    exe = str(tmp_path / "fleet_rollout")
+    pkg = os.path.join(ROOT, "nmpc_nav_control_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "fleet_rollout.cpp"), "-L", pkg, "-lnmpc_b200", "-L", os.path.join(cuda, "lib64"),
+                        "-lcudart", f"-Wl,-rpath,{pkg}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe, "8", "3"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 2 and "no CPU fallback" in p.stderr, (p.returncode, p.stderr)

@@ -1,7 +1,7 @@
 """CPU check of the CUDA solver's arithmetic against the oracle, through tests/host_emul (the kernel headers
-compiled by g++): the lane-group K3 that ships by default (rti_group.cuh; an emulated warp of 32 lanes runs
-its bulk-synchronous phases lane by lane, G lanes per instance) and the per-lane K3 (rti_core.cuh, the
-NMPC_K3=sweep path).  The structured Riccati / delta-corrector path of
+compiled by g++): the lane-cooperative K3 that ships by default (rti_coop.cuh: an emulated warp of 32 lanes runs
+its phases lane by lane, a shuffle reads the neighbour lane's register as the previous phase left it), the first
+lane-group mapping (rti_group.cuh, NMPC_GRP_IMPL=group) and the per-lane K3 (rti_core.cuh, the lockstep sweeps).  The structured Riccati / delta-corrector path of
 the kernels is a different factorisation of the same Newton systems as the oracle's dense
 square-root Riccati, so agreement is to rounding, not bit-exact; iteration counts must be equal."""
 import numpy as np
@@ -12,17 +12,36 @@ from helpers import instances, oracle_solve, parity_report
 
 
 GROUP = {"diff": 8, "tric": 8, "omni4": 16}     # lanes per instance of the shipped configuration
+KINDS = ["coop", "group", "lane"]
 
 
-@pytest.mark.parametrize("group", [True, False])
+def _emul(name, x0, yref, kind, **kw):
+    if kind == "coop":
+        return emul.emul_rti(name, x0, yref, coop=True, **kw)
+    return emul.emul_rti(name, x0, yref, group=GROUP[name] if kind == "group" else 0, **kw)
+
+
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("name,B,start", [("diff", 192, 0), ("omni4", 64, 300), ("tric", 128, 77)])
-def test_cold_step_matches_oracle(oracle_mod, name, B, start, group):
+def test_cold_step_matches_oracle(oracle_mod, name, B, start, kind):
     spec, x0, yref, _ = instances(name, start, B)
     ref = oracle_solve(oracle_mod, name, x0, yref)
-    out = emul.emul_rti(name, x0, yref, group=GROUP[name] if group else 0)
+    out = _emul(name, x0, yref, kind)
     assert (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["x"], ref["x"])[0] == 0
     assert parity_report(out["u"], ref["u"])[0] == 0
+
+
+def test_coop_slot_refill_ragged_queue(oracle_mod):
+    """more instances than slots of the emulated warps: slots are refilled from the queue as instances converge, the last
+    round is ragged and the lanes of an empty slot compute on stale images without touching global memory"""
+    for name, B in (("diff", 45), ("tric", 9), ("omni4", 5)):
+        spec, x0, yref, _ = instances(name, 2500, B)
+        ref = oracle_solve(oracle_mod, name, x0, yref)
+        out = emul.emul_rti(name, x0, yref, coop=True)
+        assert (out["qp_status"] == 0).all()
+        assert (out["qp_iter"] == ref["qp_iter"]).all(), name
+        assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, name
 
 
 def test_group_slot_refill_and_other_group_sizes(oracle_mod):
@@ -37,22 +56,23 @@ def test_group_slot_refill_and_other_group_sizes(oracle_mod):
         assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, (name, G)
 
 
+@pytest.mark.parametrize("coop", [True, False])
 @pytest.mark.parametrize("name,K,B", [("diff", 0, 40), ("diff", 5, 48), ("diff", 8, 64), ("tric", 4, 40), ("omni4", 9, 24)])
-def test_hybrid_handover(oracle_mod, name, K, B):
+def test_hybrid_handover(oracle_mod, name, K, B, coop):
     """the hybrid schedule: K iterations of the per-lane sweeps (a lane whose corrector overshoots leaves them at its
     centering repeat), record conversion, then the lane-group kernel resumes the unfinished instances in the middle of
     their iteration"""
     spec, x0, yref, _ = instances(name, 1200, B)
     ref = oracle_solve(oracle_mod, name, x0, yref)
-    out = emul.emul_rti(name, x0, yref, hybrid=K)
+    out = emul.emul_rti(name, x0, yref, hybrid=K, coop=coop)
     assert 0 < out["resumed"] <= B
     assert (out["qp_status"] == 0).all() and (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0
 
 
-@pytest.mark.parametrize("group", [True, False])
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("name", ["diff", "omni4", "tric"])
-def test_warm_steps_and_pose_only_yref(oracle_mod, name, group):
+def test_warm_steps_and_pose_only_yref(oracle_mod, name, kind):
     """three consecutive RTI steps (iterate carried over, x0 <- x1), pose-only yref in the kernel path"""
     B = 48
     spec, x0, yref3, _ = instances(name, 9000, B, pose_only=True)
@@ -61,7 +81,7 @@ def test_warm_steps_and_pose_only_yref(oracle_mod, name, group):
     x0r, x0e = x0.copy(), x0.copy()
     for step in range(3):
         ref = oracle_solve(oracle_mod, name, x0r, yfull, x=xr, u=ur)
-        out = emul.emul_rti(name, x0e, yref3, x=xe, u=ue, group=GROUP[name] if group else 0)
+        out = _emul(name, x0e, yref3, kind, x=xe, u=ue)
         assert (out["qp_iter"] == ref["qp_iter"]).all(), step
         lr = ref["lin_res"]
         assert (lr > 1e-10).sum() <= 2, step          # ill-conditioned QPs are the exception
@@ -70,18 +90,18 @@ def test_warm_steps_and_pose_only_yref(oracle_mod, name, group):
         x0r, x0e = xr[:, 1].copy(), xe[:, 1].copy()
 
 
-@pytest.mark.parametrize("group", [8, 0])
-def test_diff_per_instance_terminal_weight(oracle_mod, group):
+@pytest.mark.parametrize("kind", KINDS)
+def test_diff_per_instance_terminal_weight(oracle_mod, kind):
     B = 64
     spec, x0, yref, We = instances("diff", 100, B, terminal_hack=True)
     ref = oracle_solve(oracle_mod, "diff", x0, yref, We=We)
-    out = emul.emul_rti("diff", x0, yref, We=We, group=group)
+    out = _emul("diff", x0, yref, kind, We=We)
     assert (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["u"], ref["u"])[0] == 0
 
 
-@pytest.mark.parametrize("group", [True, False])
-def test_nondefault_tables(oracle_mod, group):
+@pytest.mark.parametrize("kind", KINDS)
+def test_nondefault_tables(oracle_mod, kind):
     """stage-varying weights / bounds / parameters set through the table setters"""
     rng = np.random.default_rng(5)
     for name in ("diff", "tric", "omni4"):
@@ -96,6 +116,6 @@ def test_nondefault_tables(oracle_mod, group):
         tb["p"] = tb["p"] * (1.0 + 0.05 * rng.random(tb["p"].shape))
         yref[:, :, 3:] = 0.1 * rng.standard_normal(yref[:, :, 3:].shape)       # full-width yref
         ref = oracle_solve(oracle_mod, name, x0, yref, tables=tb)
-        out = emul.emul_rti(name, x0, yref, tables=tb, group=GROUP[name] if group else 0)
+        out = _emul(name, x0, yref, kind, tables=tb)
         assert (out["qp_iter"] == ref["qp_iter"]).all(), name
         assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, name

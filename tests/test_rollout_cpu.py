@@ -103,3 +103,20 @@ def test_whole_tick_chain_on_the_host_matches_oracle_chain(oracle_mod, name):
             assert r["qp_iter"][i] == qi, (t, i)
             assert np.abs(cmd[:, i] - np.array(want)).max() <= 1e-9, (t, i, cmd[:, i], want)
             assert np.abs(pose[:, i] - oracles[i].pose).max() <= 1e-9, (t, i)
+
+
+def test_oracle_sqp_and_shift_protocol(oracle_mod):
+    """the SQP / warm-start-shift extension of the oracle chain (the parity target of nmpc_rollout_device with
+    sqp_max_iter > 1 and shift = 1): SQP stops on the step norm, the shift moves every stage down by one and keeps the last"""
+    from oracle.ctrl import OracleController
+    c = OracleController(oracle_mod, "tric")
+    refs = [(0.02 * k, 0.01 * k, 0.05) for k in range(c.spec.n + 1)]
+    cmd1, qp1 = c.run(np.array([0.0, 0.02, 0.0]), (0.1, 0.0, 0.0), 0.05, refs, sqp_max_iter=6, sqp_tol=1e-8)
+    assert 1 < c.sqp_steps <= 6 and qp1 > 0
+    x, u = c.x.copy(), c.u.copy()
+    c.shift()
+    assert np.array_equal(c.x[:-1], x[1:]) and np.array_equal(c.x[-1], x[-1])
+    assert np.array_equal(c.u[:-1], u[1:]) and np.array_equal(c.u[-1], u[-1])
+    c2 = OracleController(oracle_mod, "tric")
+    c2.run(np.array([0.0, 0.02, 0.0]), (0.1, 0.0, 0.0), 0.05, refs)          # the reference's single RTI step
+    assert c2.sqp_steps == 1 and np.abs(c2.u - u).max() > 1e-9

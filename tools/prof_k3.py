@@ -13,6 +13,8 @@ spec = MODELS[name]
 inst = synth.make_instances(spec, 0, B, device="cuda", pose_only=True)
 x0 = inst["x0"].t().contiguous(); yref = inst["yref"].permute(1, 2, 0).contiguous()
 s = BatchedRtiSolver(spec, B)
+if os.environ.get("PROF_ITER_MAX"):          # experiment: cap the interior-point iterations (bounds the straggler tail)
+    s.set_opts(iter_max=int(os.environ["PROF_ITER_MAX"]))
 for _ in range(reps):
     s.reset_async()
     out = s.solve_device(x0, yref)
