@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define NMPC_N 80                       /* scripts/<m>/common.py:5-9: N = ceil(tf_ini * freq) */
+#include "nmpc_horizon.h"               /* NMPC_N, NMPC_DT: scripts/<m>/common.py:5-9, N = ceil(tf_ini * freq); emitted, see emit.py.
+                                         * nmpc_dims().n is the horizon of the loaded library */
 
 enum { NMPC_MODEL_DIFF = 0, NMPC_MODEL_OMNI4 = 1, NMPC_MODEL_TRIC = 2 };
 

@@ -75,6 +75,25 @@ def build_acados_shims(force: bool = False) -> list:
     return outs
 
 
+def build_alternate(out_dir: str) -> str:
+    """libnmpc_b200.so for the horizon / default tables emitted into `out_dir` (emit.py --out-dir): the same sources with
+    out_dir/include first on the include path and out_dir/model_defaults.inc as the table"""
+    out = os.path.join(out_dir, "libnmpc_b200.so")
+    hdr = open(os.path.join(out_dir, "include", "nmpc_horizon.h")).read()
+    import re
+    n = re.search(r"#define\s+NMPC_N\s+(\d+)", hdr).group(1)
+    dt = re.search(r"#define\s+NMPC_DT\s+([0-9.eE+-]+)", hdr).group(1)
+    flags = [f"-DNMPC_N={n}", f"-DNMPC_DT={dt}"]
+    inc = os.path.join(out_dir, "model_defaults.inc")
+    if os.path.exists(inc):
+        flags.append(f'-DNMPC_MODEL_DEFAULTS_INC="{os.path.abspath(inc)}"')
+    cmd = [_nvcc()] + NVCC_FLAGS + flags + ["-o", out, os.path.join(CSRC, "rti_kernels.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build_all(force: bool = False) -> None:
     build_core(force)
     build_acados_shims(force)

@@ -5,6 +5,7 @@
 //     infrastructure: nothing in the product library or the Python package can reach it.
 #pragma once
 #include <math.h>
+#include "../../include/nmpc_horizon.h"
 
 #if defined(__CUDACC__)
 #define NMPC_HD __host__ __device__ __forceinline__
@@ -50,7 +51,8 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #endif
 
 constexpr int LANES = 32;     // instances per tile = lanes per warp
-constexpr int NSTAGE = 80;    // N: scripts/<m>/common.py:5-9 (tf_ini=2.0, freq=40)
+constexpr int NSTAGE = NMPC_N;    // N and dt: scripts/<m>/common.py:5-9, emitted into include/nmpc_horizon.h by emit.py
+constexpr double OCP_DT = NMPC_DT;
 
 // warp-wide "does any lane still want this sweep"; per-lane emulation on the host
 #if defined(__CUDA_ARCH__)

@@ -631,8 +631,11 @@ struct ModelInfo {
 };
 // config/nmpc_nav_control_acados_models.yaml:2-75 through scripts/<m>/generate_c_code.py:30-60; the table is generated by
 // `python -m nmpc_nav_control_b200.emit <yaml>`, the committed copy is the reference's YAML
+#ifndef NMPC_MODEL_DEFAULTS_INC
+#define NMPC_MODEL_DEFAULTS_INC "model_defaults.inc"
+#endif
 static const ModelInfo g_models[3] = {
-#include "model_defaults.inc"
+#include NMPC_MODEL_DEFAULTS_INC
 };
 
 // ---- plant step and nearest path parameter, one thread per robot (rollout.cuh) ---
@@ -939,7 +942,7 @@ extern "C" int nmpc_get_opts(const nmpc_solver* s, nmpc_ipm_opts* o)
 template <class M>
 static int launch_lti(nmpc_solver* s, cudaStream_t st)
 {
-    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, 1.0 / 40.0, s->d_tab + s->off_lti, s->d_tab + s->off_thr);
+    k_lti_setup<M><<<1, 128, 0, st>>>(s->d_tab + s->off_p, OCP_DT, s->d_tab + s->off_lti, s->d_tab + s->off_thr);
     CK(cudaGetLastError());
     return 0;
 }
@@ -982,7 +985,7 @@ static Tables make_tables(const nmpc_solver* s)
     tb.lbx = s->d_tab + s->off_lbx; tb.ubx = s->d_tab + s->off_ubx;
     tb.lbu = s->d_tab + s->off_lbu; tb.ubu = s->d_tab + s->off_ubu;
     tb.p = s->d_tab + s->off_p; tb.lti = s->d_tab + s->off_lti; tb.stg = s->d_tab + s->off_stg; tb.thr = s->d_tab + s->off_thr;
-    tb.dt = 1.0 / 40.0;
+    tb.dt = OCP_DT;
     return tb;
 }
 

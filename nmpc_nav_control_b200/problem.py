@@ -21,8 +21,22 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-N_HORIZON = 80
-DT = 1.0 / 40.0          # freq: 40 -> dt = 0.025, N = ceil(2.0/0.025) = 80, TF = N*dt = 2.0
+
+
+def _read_horizon():
+    """N and dt of the build this package drives: the emitted include/nmpc_horizon.h (emit.py; the reference fixes them at
+    code-generation time, scripts/<m>/common.py:5-9).  NMPC_HORIZON_H selects the header of an alternate build."""
+    import os
+    import re
+    path = os.environ.get("NMPC_HORIZON_H") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                             "include", "nmpc_horizon.h")
+    txt = open(path).read()
+    n = int(re.search(r"#define\s+NMPC_N\s+(\d+)", txt).group(1))
+    dt = float(re.search(r"#define\s+NMPC_DT\s+([0-9.eE+-]+)", txt).group(1))
+    return n, dt
+
+
+N_HORIZON, DT = _read_horizon()   # the reference's yaml: freq 40 -> dt = 0.025, N = ceil(2.0 / 0.025) = 80, TF = N dt = 2.0
 
 
 @dataclass(frozen=True)

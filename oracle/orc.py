@@ -14,8 +14,16 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ORC_N = 80
 ORC_HIST = 64
+
+
+def _horizon() -> int:
+    """the horizon the checked build was emitted for (nmpc_nav_control_b200.problem reads include/nmpc_horizon.h)"""
+    from nmpc_nav_control_b200.problem import N_HORIZON
+    return int(N_HORIZON)
+
+
+ORC_N = _horizon()
 
 _DIMS = {  # name -> (nx, nu, np, nbx, nbu)
     "diff": (7, 2, 2, 2, 2),
@@ -38,15 +46,22 @@ class Stats(C.Structure):
                 ("alpha_hist", C.c_double * ORC_HIST), ("mu_hist", C.c_double * ORC_HIST)]
 
 
+def _names():
+    """library file names: the default horizon keeps the plain names, another horizon (an alternate emitted build) gets its own"""
+    sfx = "" if ORC_N == 80 else f"_n{ORC_N}"
+    return f"liboracle{sfx}.so", f"liboracle_fast{sfx}.so"
+
+
 def build(force: bool = False) -> None:
     """compile the oracle with the Makefile next to this file (gcc only)"""
-    need = force or not all(os.path.exists(os.path.join(_HERE, f)) for f in ("liboracle.so", "liboracle_fast.so"))
+    ref, fast = _names()
+    need = force or not all(os.path.exists(os.path.join(_HERE, f)) for f in (ref, fast))
     if not need:
         srcs = [os.path.join(_HERE, f) for f in ("orc_api.c", "orc_common.h", "orc_models.h", "orc_rti_core.inc")]
         newest = max(os.path.getmtime(s) for s in srcs)
-        need = any(os.path.getmtime(os.path.join(_HERE, f)) < newest for f in ("liboracle.so", "liboracle_fast.so"))
+        need = any(os.path.getmtime(os.path.join(_HERE, f)) < newest for f in (ref, fast))
     if need:
-        subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "-B", "all", f"ORC_N={ORC_N}", f"REFLIB={ref}", f"FASTLIB={fast}"], check=True, capture_output=True)
 
 
 _libs = {}
@@ -56,7 +71,7 @@ def _lib(fast: bool):
     key = "fast" if fast else "ref"
     if key not in _libs:
         build()
-        _libs[key] = C.CDLL(os.path.join(_HERE, "liboracle_fast.so" if fast else "liboracle.so"))
+        _libs[key] = C.CDLL(os.path.join(_HERE, _names()[1] if fast else _names()[0]))
     return _libs[key]
 
 

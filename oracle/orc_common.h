@@ -8,7 +8,9 @@
 #ifndef ORC_COMMON_H
 #define ORC_COMMON_H
 
-#define ORC_N 80           /* scripts/{diff,omni4,tric}/common.py: N = ceil(tf_ini*freq) = 80 */
+#ifndef ORC_N
+#define ORC_N 80           /* scripts/{diff,omni4,tric}/common.py: N = ceil(tf_ini*freq) = 80; -DORC_N=... for another horizon */
+#endif
 #define ORC_HIST 64
 
 typedef struct {

@@ -9,19 +9,20 @@ import subprocess
 import numpy as np
 
 from nmpc_nav_control_b200 import _lib
-from nmpc_nav_control_b200.problem import MODELS
+from nmpc_nav_control_b200.problem import DT, MODELS, N_HORIZON
 
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
 _SRC = os.path.join(_HERE, "emul.cpp")
-_SO = os.path.join(_HERE, "libemul.so")
+# the horizon is a build parameter (include/nmpc_horizon.h, emitted): an alternate horizon gets its own emulation library
+_SO = os.path.join(_HERE, "libemul.so" if N_HORIZON == 80 else f"libemul_n{N_HORIZON}.so")
 _CSRC = os.path.join(os.path.dirname(_HERE), "..", "nmpc_nav_control_b200", "csrc")
 
 
 def build(force=False):
     deps = [_SRC] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DNMPC_HOST_EMUL", "-fPIC", "-shared",
-                        "-o", _SO, _SRC], check=True, capture_output=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DNMPC_HOST_EMUL", f"-DNMPC_N={N_HORIZON}", f"-DNMPC_DT={DT!r}",
+                        "-fPIC", "-shared", "-o", _SO, _SRC], check=True, capture_output=True)
     return C.CDLL(_SO)
 
 

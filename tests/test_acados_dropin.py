@@ -51,9 +51,13 @@ def test_headers_on_include_path_and_macros():
     for spec in MODELS.values():
         txt = open(os.path.join(inc, f"acados_solver_{spec.acados_name}.h")).read()
         M = spec.acados_name.upper()
-        for key, val in (("N", spec.n), ("NX", spec.nx), ("NU", spec.nu), ("NY", spec.ny), ("NYN", spec.nx),
+        for key, val in (("NX", spec.nx), ("NU", spec.nu), ("NY", spec.ny), ("NYN", spec.nx),
                          ("NP", spec.np_), ("NBX", spec.nbx), ("NBU", spec.nbu)):
             assert f"#define {M}_{key} {val}\n" in txt, (M, key)
+        # the horizon macro follows the emitted header (include/nmpc_horizon.h): evaluate it with the preprocessor
+        r = subprocess.run(["g++", "-x", "c++", "-E", "-P", "-I", inc, "-"], input=f'#include "acados_solver_{spec.acados_name}.h"\nHORIZON={M}_N\n',
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and f"HORIZON={spec.n}" in r.stdout.replace(" ", ""), (M, r.stderr[-500:])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
