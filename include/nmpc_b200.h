@@ -80,7 +80,8 @@ int nmpc_iterate_device(nmpc_solver* s, double** d_x, double** d_u, int* leading
 int nmpc_reset(nmpc_solver* s);
 /* same, enqueued on `stream` (cudaStream_t, NULL = the default stream) without host sync */
 int nmpc_reset_async(nmpc_solver* s, void* stream);
-/* instance-major host copies: x [B][N+1][nx], u [B][N][nu] */
+/* instance-major host copies: x [B][N+1][nx], u [B][N][nu].  They run on the solver's own stream and wait only for it:
+ * synchronise the stream of any device call (solve, shift, rollout) that touched the iterate before reading it back. */
 int nmpc_set_iterate_host(nmpc_solver* s, int B, const double* x, const double* u);
 int nmpc_get_iterate_host(nmpc_solver* s, int B, double* x, double* u);
 

@@ -1,10 +1,12 @@
 // K3 "coop" path: the persistent lane-cooperative primal-dual interior point, second mapping.
 //
-// Replaces (like rti_core.cuh / rti_group.cuh) what the reference reaches through
+// Replaces (like rti_core.cuh) what the reference reaches through
 // `{m}_acados_solve(capsule)` (src/nmpc_nav_control/NMPCNavControlDiff.cpp:142, Omni4.cpp:139,
 // Tric.cpp:146): the HPIPM interior-point solve of the SQP-RTI QP.
-// Same iteration path, same per-instance records (GRec), same work queue and slot logic as
-// rti_group.cuh; what changes is how the G = 4 NV lanes of an instance divide a stage:
+// Same iteration path as the per-lane sweeps of rti_core.cuh (initial point, Mehrotra predictor / corrector as predictor +
+// delta, conditional centering, step rule, exit test; the control logic Rti<M>::after_* is shared), per-instance records
+// (GRec, rti_records.cuh), a work queue that refills a slot as soon as its instance converges; the G = 4 NV lanes of an
+// instance divide a stage like this:
 //
 //  * every lane runs the SAME straight-line code; a lane's role is data (a column of E, three
 //    coefficients of the stage table, a shuffle source lane), never a branch.  Lane r < NX owns
@@ -24,7 +26,7 @@
 // Hence the one rule of this file: a field read through CO_SHFL / CO_SHFLX in a phase is never
 // written in that phase.
 #pragma once
-#include "rti_group.cuh"
+#include "rti_records.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define CO_SHFL(field, srclane) __shfl_sync(0xffffffffu, L.field, (srclane))
@@ -64,7 +66,7 @@ template <class M, int G_>
 struct Coop {
     using S = Rti<M>;
     using LaneCtl = typename S::LaneCtl;
-    using GP = Grp<M, G_>;                       // static helpers and the stage-table geometry are shared with the first mapping
+    using GP = RecOps<M>;                        // record helpers and the stage-table geometry
     static constexpr int G = G_, NSLOT = 32 / G, XM = G / 2;
     static constexpr int NV = S::NV, NX = S::NX, NU = S::NU, NZ = S::NZ, NY = S::NY, NC = S::NC, NB2 = S::NB2, NLU = S::NLU;
     static constexpr int NCT = 2 * NB2;

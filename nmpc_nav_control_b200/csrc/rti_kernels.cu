@@ -18,7 +18,6 @@
 #include <vector>
 
 #include "rti_core.cuh"
-#include "rti_group.cuh"
 #include "rti_coop.cuh"
 #include "ctrl_glue.cuh"
 #include "path_disc.cuh"
@@ -179,7 +178,7 @@ k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict_
     }
 }
 
-// ---- group path (rti_group.cuh): per-instance contiguous records -----------------------------
+// ---- persistent path (rti_coop.cuh, rti_records.cuh): per-instance contiguous records -----------
 // K1+K2 and the interior-point cold start into the group layout: block = LING_BLOCK instances of one
 // stage; the [Q, LHD) head and the [MC, NREC) tail of every record are staged in shared memory and
 // written out as contiguous runs (368 + 496 bytes for diff).
@@ -234,26 +233,10 @@ k_linearize_g(int B, int i0, int nchunk, const double* __restrict__ x0bar, const
 #ifndef NMPC_GRP_WARPS
 #define NMPC_GRP_WARPS 4
 #endif
-#ifndef NMPC_GRP_MINB
-#define NMPC_GRP_MINB 3
-#endif
-constexpr int GRP_WARPS = NMPC_GRP_WARPS;           // warps per CTA of the group kernel
+constexpr int GRP_WARPS = NMPC_GRP_WARPS;           // warps per CTA of the persistent K3 kernel
 
-// K3, group path: persistent warps, each running the whole interior-point loop of 32/G instances at a
-// time and refilling converged slots from the queue *next (instances [0, n) of the chunk).
-template <class M, int G, int MINB>
-__global__ void __launch_bounds__(GRP_WARPS * 32, MINB)
-k_ipm_group(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldWe, IpmOpts o, double* __restrict__ ws,
-            int* __restrict__ next, GrpOut out, GrpResume rs)
-{
-    using GP = Grp<M, G>;
-    extern __shared__ __align__(16) double grp_sm[];
-    typename GP::Lane L;
-    GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
-    GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out, rs);
-}
-
-// K3, coop path (rti_coop.cuh): the same persistent schedule and records, lanes cooperating through shuffles
+// K3, persistent lane-cooperative kernel (rti_coop.cuh): each warp runs the whole interior-point loop of 32/G instances
+// at a time and refills converged slots from the queue *next (instances [0, n) of the chunk, or the hand-over list)
 #ifndef NMPC_COOP_MINB
 #define NMPC_COOP_MINB 3
 #endif
@@ -428,12 +411,12 @@ __global__ void k_handover_assign(int nchunk, int ldc, const double* __restrict_
 // field slices per instance with one block per tile 3.0 ms.  The kernel reads 4.3 GB - nearly the whole tile workspace,
 // since a 32-byte sector holds four lanes and 26 % of the lanes are wanted.
 constexpr int CV_BLOCK = 64, CV_PIECES = 4;
-template <class M, int G>
+template <class M>
 __global__ void __launch_bounds__(CV_BLOCK)
 k_handover_convert(int nchunk, const int* __restrict__ map, const double* __restrict__ ws_tile, double* __restrict__ ws_grp,
                    const double* __restrict__ thr)
 {
-    using GP = Grp<M, G>;
+    using GP = RecOps<M>;
     using R = typename Rti<M>::R;
     using GR = typename GP::R;
     constexpr int PW = ((GR::NREC + CV_PIECES - 1) / CV_PIECES + 1) & ~1;     // piece width, even
@@ -700,16 +683,15 @@ __global__ void k_ctrl_post(int B, const int* __restrict__ status, const double*
 
 struct nmpc_solver {
     int model, cap, device, chunk;
-    int k3_group = 2;            // K3 schedule: 0 per-sweep kernels (rti_core.cuh), 1 lane-group persistent kernel (rti_group.cuh),
+    int k3_group = 2;            // K3 schedule: 0 per-sweep kernels (rti_core.cuh), 1 persistent lane-cooperative kernel (rti_coop.cuh),
                                  // 2 hybrid: per-sweep kernels while most instances iterate, then the group kernel for the rest
     double *d_ws_g = nullptr;    // group workspace (schedules 1, 2)
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
-    int k3_impl = 1;             // lane-group kernel: 0 first mapping (rti_group.cuh), 1 lane-cooperative mapping (rti_coop.cuh)
     int hyb_kmax = 12; double hyb_frac = 0.75;  // hand over once fewer than 75 % of the chunk iterate: a lockstep launch costs the same at any
                                  // active fraction (17.5 k instance-iterations / ms when full), the lane-cooperative kernel sustains 12.7 k
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
-    int grp_G = 0, grp_blocks = 0;
+    int grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
     int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false;
     size_t ws_doubles_per_inst = 0;
@@ -827,9 +809,6 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
     if (const char* e = getenv("NMPC_HYB_MIN")) { int v = atoi(e); if (v >= 0) s->hyb_min = v; }
     if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
-    if (const char* e = getenv("NMPC_GRP_IMPL")) s->k3_impl = !strcmp(e, "group") ? 0 : 1;
-    s->grp_G = (model == 1) ? 16 : 8;
-    if (const char* e = getenv("NMPC_GRP_G")) { int v = atoi(e); if ((v == 8 && model != 1) || v == 16 || v == 32) s->grp_G = v; }
     {
         s->ws_doubles_per_inst = s->tile_doubles / LANES;
     }
@@ -1019,7 +998,7 @@ static int launch_group_k(nmpc_solver* s, grp_kernel_t kern, int i0, int n, cons
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, GRP_WARPS * 32, smem));
-        if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_group does not fit on an SM");
+        if (nb < 1) return set_err(NMPC_E_CUDA, "k_ipm_coop does not fit on an SM");
         if (const char* e = getenv("NMPC_GRP_BPS")) { int v = atoi(e); if (v >= 1 && v < nb) nb = v; }
         blocks_per_sm = nb;
     }
@@ -1036,29 +1015,13 @@ static int launch_group_k(nmpc_solver* s, grp_kernel_t kern, int i0, int n, cons
     CK(cudaGetLastError());
     return 0;
 }
-template <class M, int G, int MINB>
-static int launch_group(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
-                        const GrpOut& out, const GrpResume& rs, cudaStream_t st)
-{
-    return launch_group_k<Grp<M, G>>(s, k_ipm_group<M, G, MINB>, i0, n, tb, d_We, ldWe, o, out, rs, st);
-}
-
 template <class M>
 static int launch_group_any(nmpc_solver* s, int i0, int n, const Tables& tb, const double* d_We, int ldWe, const IpmOpts& o,
                             const GrpOut& out, const GrpResume& rs, cudaStream_t st)
 {
     using S = Rti<M>;
-    const int G = s->grp_G;
-    if (s->k3_impl == 1)       // lane-cooperative mapping (rti_coop.cuh): G = 4 nv lanes per instance
-        return launch_group_k<Coop<M, 4 * S::NV>>(s, k_ipm_coop<M, 4 * S::NV, (S::NV == 2 ? NMPC_COOP_MINB : 2)>, i0, n, tb, d_We, ldWe, o, out, rs, st);
-    if constexpr (S::NV == 2) {
-        if (G == 8) return launch_group<M, 8, NMPC_GRP_MINB>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
-        if (G == 16) return launch_group<M, 16, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
-        return launch_group<M, 32, 3>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
-    } else {
-        if (G == 32) return launch_group<M, 32, 2>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
-        return launch_group<M, 16, 2>(s, i0, n, tb, d_We, ldWe, o, out, rs, st);
-    }
+    // G = 4 nv lanes per instance; 12 warps / SM for nv = 2 (168 registers), 8 for nv = 4 (no spills at 244 registers)
+    return launch_group_k<Coop<M, 4 * S::NV>>(s, k_ipm_coop<M, 4 * S::NV, (S::NV == 2 ? NMPC_COOP_MINB : 2)>, i0, n, tb, d_We, ldWe, o, out, rs, st);
 }
 
 template <class M>
@@ -1116,9 +1079,7 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
                 k_handover_count<<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, s->d_map);
                 k_handover_assign<M><<<(n + 255) / 256, 256, 0, st>>>(n, ldc, s->d_ctl_d, s->d_ctl_i, bcnt, nres, s->d_list, s->d_map, s->d_ctl_g);
                 dim3 gc((n + CV_BLOCK - 1) / CV_BLOCK, NSTAGE + 1);
-                if (s->grp_G == 16) k_handover_convert<M, 16><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
-                else if (s->grp_G == 32) k_handover_convert<M, 32><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
-                else if constexpr (S::NV == 2) k_handover_convert<M, 8><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
+                k_handover_convert<M><<<gc, CV_BLOCK, 0, st>>>(n, s->d_map, s->d_ws, s->d_ws_g, tb.thr);
                 const GrpOut out{s->d_qp_status, d_qp_iter, d_stats, B};
                 rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, GrpResume{nres, s->d_list, s->d_ctl_g}, st);
                 if (rc) return rc;

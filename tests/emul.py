@@ -39,11 +39,11 @@ def default_opts():
     return o
 
 
-def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, group=0, hybrid=None, coop=False):
+def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, hybrid=None, coop=False):
     """one RTI step of B instances through the emulated kernel logic; returns dict like the oracle helper.
-    group = 0: the per-lane K3 of rti_core.cuh; group = G: the lane-group K3 of rti_group.cuh with G lanes per instance;
-    hybrid = K: K iterations of the per-lane sweeps, then hand-over of the unfinished instances to the lane-group kernel
-    (returns the number handed over as out["resumed"])"""
+    coop = False: the per-lane K3 of rti_core.cuh (the lockstep sweeps); coop = True: the persistent lane-cooperative K3 of
+    rti_coop.cuh (G = 4 nv lanes per instance); hybrid = K: K iterations of the per-lane sweeps, then hand-over of the
+    unfinished instances to the lane-cooperative kernel (returns the number handed over as out["resumed"])"""
     lib = build()
     spec = MODELS[name]
     tb = tables or spec.codegen_defaults()
@@ -57,11 +57,9 @@ def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, gr
     o = opts or default_opts()
     x0 = np.ascontiguousarray(x0, dtype=np.float64); yref = np.ascontiguousarray(yref, dtype=np.float64)
     we = None if We is None else np.ascontiguousarray(We, dtype=np.float64)
-    fn, lead = (lib.emul_rti, ()) if not group else (lib.emul_rti_group, (C.c_int(group),))
-    if coop:                       # the lane-cooperative K3 of rti_coop.cuh (G = 4 nv lanes per instance)
-        fn, lead = lib.emul_rti_coop, (C.c_int(0),)
+    fn, lead = (lib.emul_rti_coop, (C.c_int(0),)) if coop else (lib.emul_rti, ())
     if hybrid is not None:
-        fn, lead = lib.emul_rti_hybrid, (C.c_int(hybrid), C.c_int(int(coop)))
+        fn, lead = lib.emul_rti_hybrid, (C.c_int(hybrid),)
     rc = fn(C.c_int(spec.model_id), *lead, C.c_int(B), _dp(arrs["W"]), _dp(arrs["We"]), _dp(arrs["lbx"]), _dp(arrs["ubx"]),
                       _dp(arrs["lbu"]), _dp(arrs["ubu"]), _dp(arrs["p"]), C.c_double(tb["dt"]), C.byref(o),
                       _dp(x0), _dp(yref), C.c_int(nyref), None if we is None else _dp(we), _dp(x), _dp(u),

@@ -6,7 +6,6 @@
 #include <cstring>
 #include <cstdlib>
 #include "../../nmpc_nav_control_b200/csrc/rti_core.cuh"
-#include "../../nmpc_nav_control_b200/csrc/rti_group.cuh"
 #include "../../nmpc_nav_control_b200/csrc/rti_coop.cuh"
 
 using namespace nmpc;
@@ -64,7 +63,7 @@ extern "C" int emul_rti(int model, int B, const double* W, const double* We, con
     return -1;
 }
 
-// ---- the lane-group K3 (rti_group.cuh): one emulated warp of 32 lanes, phases run lane by lane ----
+// ---- the persistent lane-cooperative K3 (rti_coop.cuh): one emulated warp of 32 lanes, phases run lane by lane ----
 template <class M, class GP>
 static int run_group(int B, const double* W, const double* We, const double* lbx, const double* ubx,
                      const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
@@ -125,24 +124,6 @@ static int run_group(int B, const double* W, const double* We, const double* lbx
     return 0;
 }
 
-extern "C" int emul_rti_group(int model, int G, int B, const double* W, const double* We, const double* lbx, const double* ubx,
-                              const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
-                              const double* x0bar, const double* yref, int nyref, const double* We_inst,
-                              double* x, double* u, int* status, int* iters, double* stats)
-{
-#define RG(MODEL, GG) return run_group<MODEL, Grp<MODEL, GG>>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats)
-    if (model == 0 && G == 8) RG(DiffModel, 8);
-    if (model == 0 && G == 16) RG(DiffModel, 16);
-    if (model == 0 && G == 32) RG(DiffModel, 32);
-    if (model == 1 && G == 16) RG(Omni4Model, 16);
-    if (model == 1 && G == 32) RG(Omni4Model, 32);
-    if (model == 2 && G == 8) RG(TricModel, 8);
-    if (model == 2 && G == 16) RG(TricModel, 16);
-    if (model == 2 && G == 32) RG(TricModel, 32);
-#undef RG
-    return -1;
-}
-
 extern "C" int emul_rti_coop(int model, int G, int B, const double* W, const double* We, const double* lbx, const double* ubx,
                              const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
                              const double* x0bar, const double* yref, int nyref, const double* We_inst,
@@ -158,7 +139,7 @@ extern "C" int emul_rti_coop(int model, int G, int B, const double* W, const dou
 }
 
 // ---- hybrid schedule: K iterations of the per-lane sweeps, then the unfinished instances are handed to the
-// lane-group kernel in the middle of an iteration (what solve_device_hybrid does on the device) ----
+// lane-cooperative kernel in the middle of an iteration (what the hybrid schedule does on the device) ----
 template <class M, class GP>
 static int run_hybrid(int K, int B, const double* W, const double* We, const double* lbx, const double* ubx,
                       const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
@@ -244,21 +225,15 @@ static int run_hybrid(int K, int B, const double* W, const double* We, const dou
     return nres;
 }
 
-extern "C" int emul_rti_hybrid(int model, int K, int coop, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+extern "C" int emul_rti_hybrid(int model, int K, int B, const double* W, const double* We, const double* lbx, const double* ubx,
                                const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
                                const double* x0bar, const double* yref, int nyref, const double* We_inst,
                                double* x, double* u, int* status, int* iters, double* stats)
 {
-#define RH(MODEL, TMPL, GG) return run_hybrid<MODEL, TMPL<MODEL, GG>>(K, B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats)
-    if (coop) {
-        if (model == 0) RH(DiffModel, Coop, 8);
-        if (model == 1) RH(Omni4Model, Coop, 16);
-        if (model == 2) RH(TricModel, Coop, 8);
-    } else {
-        if (model == 0) RH(DiffModel, Grp, 8);
-        if (model == 1) RH(Omni4Model, Grp, 16);
-        if (model == 2) RH(TricModel, Grp, 8);
-    }
+#define RH(MODEL, GG) return run_hybrid<MODEL, Coop<MODEL, GG>>(K, B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats)
+    if (model == 0) RH(DiffModel, 8);
+    if (model == 1) RH(Omni4Model, 16);
+    if (model == 2) RH(TricModel, 8);
 #undef RH
     return -1;
 }

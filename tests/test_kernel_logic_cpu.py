@@ -1,7 +1,7 @@
 """CPU check of the CUDA solver's arithmetic against the oracle, through tests/host_emul (the kernel headers
 compiled by g++): the lane-cooperative K3 that ships by default (rti_coop.cuh: an emulated warp of 32 lanes runs
-its phases lane by lane, a shuffle reads the neighbour lane's register as the previous phase left it), the first
-lane-group mapping (rti_group.cuh, NMPC_GRP_IMPL=group) and the per-lane K3 (rti_core.cuh, the lockstep sweeps).  The structured Riccati / delta-corrector path of
+its phases lane by lane, a shuffle reads the neighbour lane's register as the previous phase left it) and the per-lane K3
+(rti_core.cuh, the lockstep sweeps of the hybrid schedule).  The structured Riccati / delta-corrector path of
 the kernels is a different factorisation of the same Newton systems as the oracle's dense
 square-root Riccati, so agreement is to rounding, not bit-exact; iteration counts must be equal."""
 import numpy as np
@@ -11,14 +11,11 @@ import emul
 from helpers import instances, oracle_solve, parity_report
 
 
-GROUP = {"diff": 8, "tric": 8, "omni4": 16}     # lanes per instance of the shipped configuration
-KINDS = ["coop", "group", "lane"]
+KINDS = ["coop", "lane"]
 
 
 def _emul(name, x0, yref, kind, **kw):
-    if kind == "coop":
-        return emul.emul_rti(name, x0, yref, coop=True, **kw)
-    return emul.emul_rti(name, x0, yref, group=GROUP[name] if kind == "group" else 0, **kw)
+    return emul.emul_rti(name, x0, yref, coop=(kind == "coop"), **kw)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -44,27 +41,14 @@ def test_coop_slot_refill_ragged_queue(oracle_mod):
         assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, name
 
 
-def test_group_slot_refill_and_other_group_sizes(oracle_mod):
-    """more instances than slots of the emulated warps (slots are refilled from the queue as instances converge,
-    ragged last round), and the wider groups (16 / 32 lanes per instance) of the same template"""
-    for name, G, B in (("diff", 8, 45), ("diff", 16, 21), ("tric", 32, 7), ("omni4", 32, 5)):
-        spec, x0, yref, _ = instances(name, 2500, B)
-        ref = oracle_solve(oracle_mod, name, x0, yref)
-        out = emul.emul_rti(name, x0, yref, group=G)
-        assert (out["qp_status"] == 0).all()
-        assert (out["qp_iter"] == ref["qp_iter"]).all(), (name, G)
-        assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0, (name, G)
-
-
-@pytest.mark.parametrize("coop", [True, False])
 @pytest.mark.parametrize("name,K,B", [("diff", 0, 40), ("diff", 5, 48), ("diff", 8, 64), ("tric", 4, 40), ("omni4", 9, 24)])
-def test_hybrid_handover(oracle_mod, name, K, B, coop):
+def test_hybrid_handover(oracle_mod, name, K, B):
     """the hybrid schedule: K iterations of the per-lane sweeps (a lane whose corrector overshoots leaves them at its
-    centering repeat), record conversion, then the lane-group kernel resumes the unfinished instances in the middle of
+    centering repeat), record conversion, then the lane-cooperative kernel resumes the unfinished instances in the middle of
     their iteration"""
     spec, x0, yref, _ = instances(name, 1200, B)
     ref = oracle_solve(oracle_mod, name, x0, yref)
-    out = emul.emul_rti(name, x0, yref, hybrid=K, coop=coop)
+    out = emul.emul_rti(name, x0, yref, hybrid=K)
     assert 0 < out["resumed"] <= B
     assert (out["qp_status"] == 0).all() and (out["qp_iter"] == ref["qp_iter"]).all()
     assert parity_report(out["x"], ref["x"])[0] == 0 and parity_report(out["u"], ref["u"])[0] == 0

@@ -26,11 +26,12 @@ def main(path, json_out=None, model=None, batch=None):
     tot = 0.0
     k3_bytes = 0.0; k3_ms = 0.0
     step = -1; step_bytes = {}; step_ms = {}; step_n = {}      # per solver step (a step starts at its linearise kernel)
+    step_fl = {}                                                # executed fp64 flops of the K3 launches (dadd + dmul + 2 dfma thread instructions)
     names = {'0': 'B_first', '1': 'B', '2': 'F', '3': 'Bd', '4': 'Fd', '5': 'FDF'}
     for (i, k), m in data.items():
         kind = re.search(r'k_sweep<([\w:]+), (?:\(int\))?(\d)>', k)
-        grp = 'k_ipm_group' in k or 'k_handover' in k or 'k_ipm_finish' in k
-        name = names[kind.group(2)] if kind else ('K3group' if 'k_ipm_group' in k else k[:24])
+        grp = 'k_ipm_group' in k or 'k_ipm_coop' in k or 'k_handover' in k or 'k_ipm_finish' in k
+        name = names[kind.group(2)] if kind else ('K3group' if 'k_ipm_group' in k else 'K3coop' if 'k_ipm_coop' in k else k[:24])
         if 'k_linearize' in k:
             step += 1
         t = num(m, 'gpu__time_duration.sum'); rd = num(m, 'dram__bytes_read.sum'); wr = num(m, 'dram__bytes_write.sum')
@@ -40,6 +41,9 @@ def main(path, json_out=None, model=None, batch=None):
             if step >= 0:
                 step_bytes[step] = step_bytes.get(step, 0.0) + rd + wr; step_ms[step] = step_ms.get(step, 0.0) + t
                 step_n[step] = step_n.get(step, 0) + 1
+                fl = (num(m, 'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum') + num(m, 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum')
+                      + 2.0 * num(m, 'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum'))
+                step_fl[step] = step_fl.get(step, 0.0) + fl
         extra = ''
         for key, lab in (('smsp__inst_executed.sum', 'inst'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'),
                          ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
@@ -56,6 +60,11 @@ def main(path, json_out=None, model=None, batch=None):
         q = 0      # the first step of the capture is complete (the last one may be cut by ncu -c)
         json.dump({"model": model, "batch": batch, "dram_bytes_per_step": step_bytes[q], "k3_ms_under_ncu": step_ms[q],
                    "k3_launches_per_step": step_n[q], "source": path}, open(json_out, "w"), indent=1)
+        if step_fl.get(q, 0.0) > 0.0:
+            import os
+            json.dump({"model": model, "batch": batch, "flops_per_step": step_fl[q], "source": path,
+                       "what": "smsp__sass_thread_inst_executed_op_{dadd,dmul}_pred_on + 2 x ..._dfma_pred_on summed over the K3 launches of one step"},
+                      open(os.path.join(os.path.dirname(json_out), "k3_exec_flops.json"), "w"), indent=1)
 
 
 if __name__ == '__main__':

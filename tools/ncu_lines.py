@@ -10,7 +10,7 @@ import csv, re, sys, collections
 
 def main():
     sass_csv, disasm, kern = sys.argv[1:4]
-    fsub = sys.argv[4] if len(sys.argv) > 4 else "rti_group.cuh"
+    fsub = sys.argv[4] if len(sys.argv) > 4 else "rti_coop.cuh"
     # address -> (file, line) from nvdisasm -g
     amap = {}
     cur = None
