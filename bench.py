@@ -3,7 +3,7 @@
 
 A "step" = one SQP-RTI iteration of every instance of the batch from the reset (all-zero)
 iterate: K1+K2 linearise, K3 interior-point QP (hybrid schedule: lockstep horizon sweeps while most
-instances iterate, then the persistent lane-group kernel for the rest), K4 step.  Workload at N=1: BASELINE config 2
+instances iterate, then the persistent lane-cooperative kernel for the rest), K4 step.  Workload at N=1: BASELINE config 2
 (diff model, 65,536 random initial states / reference paths, SURVEY.md Appendix D inputs).
 With N>1 every rank solves its own 65,536-instance shard (weak scaling, no collective on the
 solve path; torch.distributed is only used for the barrier and the max-over-ranks time).
@@ -423,7 +423,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e, "api": "nmpc_rti_solve_host (C ABI, pinned host buffers)"},
         "gpu_launches": launches,
         "kernel_ms": kt,
-        "roofline": {"kernel": "K3 interior point = the k_sweep<B_FIRST|FDF|B>, k_handover_* and k_ipm_group launches of one step", "bound": "hbm",
+        "roofline": {"kernel": "K3 interior point = the k_sweep<B_FIRST|FDF|B>, k_handover_* and k_ipm_coop launches of one step", "bound": "hbm",
                      "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": alg_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                      "note": "achieved = algorithmic bytes (17,512 B/solve, SURVEY 8d) x instances / K3 time per step "
