@@ -31,6 +31,9 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #ifndef NMPC_FDF_MINB
 #define NMPC_FDF_MINB 16                // resident single-warp CTAs per SM the solve-sweep kernel is compiled for (16: 128 registers)
 #endif
+#ifndef NMPC_B_MINB
+#define NMPC_B_MINB 8                   // resident single-warp CTAs per SM the factorising sweep is compiled for (8: 255 registers)
+#endif
 #ifndef NMPC_FDF_PREFETCH
 #define NMPC_FDF_PREFETCH 0             // 1: the solve sweeps prefetch the next stage's fields into L2 (rti_core.cuh sweep_lane)
 #endif
@@ -48,6 +51,17 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #define NMPC_PHASE_FENCE() asm volatile("" ::: "memory")
 #else
 #define NMPC_PHASE_FENCE() ((void)0)
+#endif
+
+// Register economy of the factorising per-lane sweep for models with at least this many channels (omni4; rti_core.cuh):
+// the update half of a stage is streamed channel by channel, and compiler fences between the columns of the Riccati
+// congruence bound how far the loads of later columns are hoisted.  omni4: 3.5 KB -> 0.9 KB of spill stores per thread,
+// 6.95 -> 5.75 ms per launch of 65,536 instances; diff / tric are faster in the whole-stage formulation (profiles/README_r02_notes.txt)
+#ifndef NMPC_B_STREAM_MINNV
+#define NMPC_B_STREAM_MINNV 4
+#endif
+#ifndef NMPC_RICCATI_FENCE_MINNV
+#define NMPC_RICCATI_FENCE_MINNV 4
 #endif
 
 constexpr int LANES = 32;     // instances per tile = lanes per warp

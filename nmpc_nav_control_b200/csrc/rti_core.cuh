@@ -86,6 +86,13 @@ struct Rec {
 // pipeline) or straight into the tile (host emulation / K1 / K4); field stride is LANES
 struct StageIn { const double *lin, *it, *st, *fa; };
 struct StageOut { double *it, *st, *fa; };
+#if defined(__CUDACC__)
+#define NMPC_RESTRICT __restrict__
+#else
+#define NMPC_RESTRICT
+#endif
+struct StageInR { const double* NMPC_RESTRICT lin; const double* NMPC_RESTRICT it; const double* NMPC_RESTRICT st; };
+struct StageOutR { double* NMPC_RESTRICT it; };
 
 template <class R>
 NMPC_HD StageOut tile_stage_out(double* tile_lane, int k)
@@ -135,6 +142,7 @@ struct Rti {
     static constexpr int NC = 1 + 3 * NV, NB2 = 2 * NV, NPK = NX * (NX + 1) / 2, NLU = NV * (NV + 1) / 2;
     static constexpr int NCON = 2 * (NV + (NSTAGE - 1) * NB2 + NV);   // one-sided constraints
     static constexpr int PSTRIDE = NMPC_SCRATCH_STRIDE;               // element stride of the per-lane scratch column
+    static constexpr bool RICCATI_FENCES = NV >= NMPC_RICCATI_FENCE_MINNV;
     using R = Rec<NV, M::THETA_ROW_LTI ? 2 : 3>;
     using L = Lin<NV>;
 
@@ -482,7 +490,12 @@ struct Rti {
     // Leaves the stage gradient (incl. barrier terms) in gu/gx, the dynamics residual in rb and the
     // barrier Hessian terms in Gam.
     // reads : LIN[all], IT[all], ST[DZ, MC] (not when first)      writes: IT[all]
-    NMPC_HD static void stage_B_update(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+    //
+    // Two formulations of the same arithmetic.  Whole stage (this one; diff, tric): every input of the stage is loaded up
+    // front, one memory round trip per stage, ~400 bytes of spills that stay in L1.  Streamed (below; omni4): channel by
+    // channel, few values live, several dependent round trips per stage.  Measured, 65,536 instances, K3 per step: diff
+    // 34.5 ms whole / 37.7 ms streamed, tric 23.6 / 27.1, omni4 139 / 119 (whole-stage omni4 spills 1.9 KB in this half alone).
+    NMPC_HD static void stage_B_update_whole(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
                                        const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
                                        double* gu, double* gx, double* rb, double* Gam)
     {
@@ -653,6 +666,226 @@ struct Rti {
         for (int j = 0; j < NX; j++) { sc[(C::SC_PIO + j) * PSTRIDE] = pi_old[j]; sc[(C::SC_XN + j) * PSTRIDE] = zx[j]; }
     }
 
+    // The streamed formulation: channel by channel, to keep few values live.  Everything a channel c = {control c,
+    // actual c, ref c} needs from the rest of the stage is the pose part of the successor's multipliers (p0, d0) and, for
+    // the dynamics residual, three running sums of the pose rows of [A B] z.  One bounded component (control or reference state):
+    struct Bnd { double ldo, dld, lnew, gam, Gam, znew; };
+    NMPC_HD static void bound_component(bool act, bool first, int b, double zb, double dzb, const StageInR& in, const StageOutR& out,
+                                        const IpmOpts& o, double a_step, double sigmu, double mcw, CarryB& cy, Bnd& r)
+    {
+        double ll, lu, tl, tu;
+        r.ldo = 0.0; r.dld = 0.0; r.znew = zb;
+        if (!act) {
+            ll = 0.0; lu = 0.0; tl = 1.0; tu = 1.0;
+            r.lnew = 0.0; r.gam = 0.0; r.Gam = 0.0;
+            if (first) r.znew = 0.0;
+        } else {
+            const double dl = in.lin[(R::DLB + b) * LANES], du_ = in.lin[(R::DUB + b) * LANES];
+            if (first) {
+                // cold start (HPIPM INIT_VAR with warm_start = 0): slacks from the bounds with the thr0 projection, lam = mu0 / t
+                double z0 = 0.0, t_l = -dl, t_u = du_;
+                if (t_l < o.thr0) {
+                    if (t_u < o.thr0) { z0 = 0.5 * (dl + du_); t_l = o.thr0; t_u = o.thr0; }
+                    else { t_l = o.thr0; z0 = dl + o.thr0; }
+                } else if (t_u < o.thr0) { t_u = o.thr0; z0 = du_ - o.thr0; }
+                r.znew = z0; tl = t_l; tu = t_u; ll = o.mu0 / t_l; lu = o.mu0 / t_u;
+            } else {
+                ll = in.it[(R::LAM + b) * LANES]; lu = in.it[(R::LAM + NB2 + b) * LANES];
+                tl = in.it[(R::T + b) * LANES];   tu = in.it[(R::T + NB2 + b) * LANES];
+                const double mc_l = in.st[(R::MC + b) * LANES], mc_u = in.st[(R::MC + NB2 + b) * LANES];
+                const double rd_l = dl - zb + tl, rd_u = -du_ + zb + tu;
+                const double rm_l = ll * tl - o.tau_min + mcw * mc_l - sigmu;
+                const double rm_u = lu * tu - o.tau_min + mcw * mc_u - sigmu;
+                const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
+                const double dl_l = -(ll * dt_l + rm_l) / tl;
+                const double dl_u = -(lu * dt_u + rm_u) / tu;
+                r.ldo = lu - ll;
+                r.dld = dl_l - dl_u;
+                ll += a_step * dl_l; lu += a_step * dl_u;
+                tl += a_step * dt_l; tu += a_step * dt_u;
+                r.znew = zb + a_step * dzb;
+            }
+            // residuals at the new iterate
+            const double zn = r.znew;
+            const double rd_l = dl - zn + tl, rd_u = -du_ + zn + tu;
+            const double pm_l = ll * tl, pm_u = lu * tu;
+            cy.musum += pm_l + pm_u;
+            const double rm_l = pm_l - o.tau_min, rm_u = pm_u - o.tau_min;
+            cy.nd = fmax(cy.nd, fmax(fabs(rd_l), fabs(rd_u)));
+            cy.nm = fmax(cy.nm, fmax(fabs(rm_l), fabs(rm_u)));
+            const double ti_l = tl < o.t_min ? 1.0 / o.t_min : 1.0 / tl;
+            const double ti_u = tu < o.t_min ? 1.0 / o.t_min : 1.0 / tu;
+            const double l_l = ll < o.lam_min ? o.lam_min : ll;
+            const double l_u = lu < o.lam_min ? o.lam_min : lu;
+            r.Gam = ti_l * l_l + ti_u * l_u;
+            r.gam = ti_l * (rm_l - ll * rd_l) - ti_u * (rm_u - lu * rd_u);
+            r.lnew = lu - ll;
+        }
+        out.it[(R::LAM + b) * LANES] = ll; out.it[(R::LAM + NB2 + b) * LANES] = lu;
+        out.it[(R::T + b) * LANES] = tl;   out.it[(R::T + NB2 + b) * LANES] = tu;
+    }
+    // one state component j: stationarity residual of the Newton system (= multiplier step of the dynamics that define x_k,
+    // the adjoint recursion), new iterate, gradient at the new iterate.  v1 / v2: component j of [B A]' (old multipliers /
+    // multiplier step of the successor).  bn: the bounded-component terms (reference states), else nullptr.
+    NMPC_HD static double state_component(int k, int j, bool first, double v1, double v2, double H, const Bnd* bn,
+                                          const StageInR& in, const StageOutR& out, double a_step, CarryB& cy, double& gxj)
+    {
+        using C = CarryB;
+        const bool hasX = k > 0;
+        double* sc = cy.sc;
+        const double qx = in.lin[(R::Q + NU + j) * LANES];
+        double zx, pin = 0.0, pi_old = 0.0;
+        if (first) {
+            zx = hasX ? (bn ? bn->znew : 0.0) : in.it[(R::Z + NU + j) * LANES];
+            sc[(C::SC_DPI + j) * PSTRIDE] = 0.0;
+        } else {
+            zx = in.it[(R::Z + NU + j) * LANES];
+            if (hasX) {
+                const double dzx = in.st[(R::DZ + NU + j) * LANES];
+                pin = in.it[(R::PI + j) * LANES];
+                pi_old = pin;
+                double r = qx + H * zx - pin + v1 + H * dzx + v2;
+                if (bn) r += bn->ldo - bn->dld;
+                sc[(C::SC_DPI + j) * PSTRIDE] = r;
+                pin += a_step * r;
+                zx = bn ? bn->znew : zx + a_step * dzx;
+            }
+        }
+        double g = qx + H * zx - pin + (v1 + a_step * v2);
+        if (bn) g += bn->lnew;
+        if (hasX) cy.ng = fmax(cy.ng, fabs(g));
+        if (bn) g += bn->gam;
+        gxj = g;
+        if (hasX) { out.it[(R::Z + NU + j) * LANES] = zx; out.it[(R::PI + j) * LANES] = pin; }
+        sc[(C::SC_PIO + j) * PSTRIDE] = pi_old;
+        return zx;
+    }
+    NMPC_HD static void stage_B_update_streamed(int k, const StageIn& in_, const StageOut& out_, const Tables& tb, const double* We,
+                                       const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
+                                       double* gu, double* gx, double* rb, double* Gam)
+    {
+        using C = CarryB;
+        const bool hasU = k < NSTAGE, hasX = k > 0;
+        double* sc = cy.sc;
+        // no field of the stage is read after it has been written: the loads may move above the stores
+        const StageInR in = {in_.lin, in_.it, in_.st};
+        const StageOutR out = {out_.it};
+        const double* lti = tb.lti + (hasU ? k : 0) * 4 * NV;
+        const double* thr = tb.thr + (hasU ? k : 0) * NC;
+        const double* Wk = tb.W + (hasU ? k : 0) * NY;
+        // entry (i, c) of the pose rows of [A | B] (columns theta | actual | ref | u); nothing is linearised at stage N
+#define EL_(i, c) (hasU ? ((i) < R::ER ? in.lin[(R::E + (i) * NC + (c)) * LANES] : thr[c]) : 0.0)
+        // pose part of the successor's carries; the successor's state for the dynamics residual
+        double p0[3], d0[3], xo[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            p0[i] = sc[(C::SC_PIO + i) * PSTRIDE]; d0[i] = sc[(C::SC_DPI + i) * PSTRIDE]; xo[i] = sc[(C::SC_XN + i) * PSTRIDE];
+        }
+        // ---- pose components x, y, theta: unit columns for x and y ---------------------------------------------------------
+        double acc[3];                       // pose rows of [A B] z at the new iterate
+        {
+            const double e0 = EL_(0, 0), e1 = EL_(1, 0), e2 = EL_(2, 0);
+            double zp[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double v1 = hasU ? (j < 2 ? p0[j] : e0 * p0[0] + e1 * p0[1] + e2 * p0[2]) : 0.0;
+                const double v2 = hasU ? (j < 2 ? d0[j] : e0 * d0[0] + e1 * d0[1] + e2 * d0[2]) : 0.0;
+                const double H = hasU ? tb.dt * Wk[j] : We[j];
+                zp[j] = state_component(k, j, first, v1, v2, H, nullptr, in, out, a_step, cy, gx[j]);
+            }
+            acc[0] = zp[0] + e0 * zp[2]; acc[1] = zp[1] + e1 * zp[2]; acc[2] = e2 * zp[2];
+#pragma unroll
+            for (int i = 0; i < 3; i++) sc[(C::SC_XN + i) * PSTRIDE] = zp[i];
+        }
+        // ---- the channels ---------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            NMPC_PHASE_FENCE();
+            const int ja = 3 + c, jr = 3 + NV + c;
+            const double pa = sc[(C::SC_PIO + ja) * PSTRIDE], pr = sc[(C::SC_PIO + jr) * PSTRIDE];
+            const double da = sc[(C::SC_DPI + ja) * PSTRIDE], dr = sc[(C::SC_DPI + jr) * PSTRIDE];
+            const double xa = sc[(C::SC_XN + ja) * PSTRIDE], xr = sc[(C::SC_XN + jr) * PSTRIDE];
+            const double av = hasU ? lti[c] : 0.0, ar = hasU ? lti[NV + c] : 0.0, au = hasU ? lti[2 * NV + c] : 0.0, ru = hasU ? lti[3 * NV + c] : 0.0;
+            // control c
+            double zun = 0.0;
+            {
+                const int q = 1 + 2 * NV + c;
+                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + au * pa + ru * pr;
+                const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + au * da + ru * dr;
+                const double H = hasU ? tb.dt * Wk[NX + c] : 0.0;
+                const double qu = in.lin[(R::Q + c) * LANES];
+                const double zu = first ? 0.0 : in.it[(R::Z + c) * LANES];
+                const double dzu = (!first && hasU) ? in.st[(R::DZ + c) * LANES] : 0.0;
+                Bnd bn;
+                bound_component(hasU, first, c, zu, dzu, in, out, o, a_step, sigmu, mcw, cy, bn);
+                if (!first && hasU) {
+                    // stationarity residual of the Newton system, control rows (diagnostic: the quantity HPIPM's
+                    // iterative refinement would test)
+                    const double r = qu + H * zu + bn.ldo + v1 + H * dzu - bn.dld + v2;
+                    cy.lru = fmax(cy.lru, fabs(r));
+                }
+                zun = bn.znew;
+                double g = qu + H * zun + bn.lnew + (v1 + a_step * v2);
+                if (hasU) cy.ng = fmax(cy.ng, fabs(g));
+                gu[c] = g + bn.gam;
+                Gam[c] = bn.Gam;
+                out.it[(R::Z + c) * LANES] = zun;
+                acc[0] += e0 * zun; acc[1] += e1 * zun; acc[2] += e2 * zun;
+            }
+            // actual c
+            double zan;
+            {
+                const int q = 1 + c;
+                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + av * pa;
+                const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + av * da;
+                const double H = hasU ? tb.dt * Wk[ja] : We[ja];
+                zan = state_component(k, ja, first, v1, v2, H, nullptr, in, out, a_step, cy, gx[ja]);
+                acc[0] += e0 * zan; acc[1] += e1 * zan; acc[2] += e2 * zan;
+            }
+            // reference c (bounded)
+            double zrn;
+            {
+                const int q = 1 + NV + c;
+                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + ar * pa + pr;
+                const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + ar * da + dr;
+                const double H = hasU ? tb.dt * Wk[jr] : We[jr];
+                const double zr = (first || !hasX) ? 0.0 : in.it[(R::Z + NU + jr) * LANES];
+                const double dzr = (first || !hasX) ? 0.0 : in.st[(R::DZ + NU + jr) * LANES];
+                Bnd bn;
+                bound_component(hasX, first, NV + c, zr, dzr, in, out, o, a_step, sigmu, mcw, cy, bn);
+                zrn = state_component(k, jr, first, v1, v2, H, hasX ? &bn : nullptr, in, out, a_step, cy, gx[jr]);
+                Gam[NV + c] = bn.Gam;
+                acc[0] += e0 * zrn; acc[1] += e1 * zrn; acc[2] += e2 * zrn;
+            }
+            // the channel's two rows of the dynamics residual
+            if (hasU) {
+                rb[ja] = av * zan + ar * zrn + au * zun + (in.lin[(R::B0 + ja) * LANES] - xa);
+                rb[jr] = zrn + ru * zun + (in.lin[(R::B0 + jr) * LANES] - xr);
+                cy.nb = fmax(cy.nb, fmax(fabs(rb[ja]), fabs(rb[jr])));
+            }
+            sc[(C::SC_XN + ja) * PSTRIDE] = zan; sc[(C::SC_XN + jr) * PSTRIDE] = zrn;
+        }
+        if (hasU) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                rb[i] = acc[i] + (in.lin[(R::B0 + i) * LANES] - xo[i]);
+                cy.nb = fmax(cy.nb, fabs(rb[i]));
+            }
+        }
+#undef EL_
+    }
+
+    NMPC_HD static void stage_B_update(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
+                                       const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
+                                       double* gu, double* gx, double* rb, double* Gam)
+    {
+        if (NV >= NMPC_B_STREAM_MINNV) stage_B_update_streamed(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
+        else stage_B_update_whole(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
+    }
+
     // phase 2 of a B stage: one step of the Riccati recursion.
     // reads : LIN[E]      writes: FA[LUU,KH,LH,RB]
     NMPC_HD static void stage_B_riccati(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
@@ -687,9 +920,11 @@ struct Rti {
             // M = [B A]' P [B A] + diag(H + Gamma + reg), built column by column in z order [u; x].
             // Control columns first: Muu (packed lower) and Mxu, then the Cholesky of Muu; the state
             // columns are folded straight into this stage's P (Schur complement), one at a time.
-            double Muu[NLU], Kh[NV][NX];
+            double Muu[NLU];
+            double Kh[NV][NX];
 #pragma unroll
             for (int a = 0; a < NV; a++) {
+                if (RICCATI_FENCES) NMPC_PHASE_FENCE();
                 double g[NX], cu[NV], cx[NX];
                 P_col_s(P, lin, a, g);
                 apply_T(lin, g, cu, cx);
@@ -731,26 +966,32 @@ struct Rti {
             if (hasX) {
 #pragma unroll
                 for (int j = 0; j < NX; j++) {
+                    double kj[NV];
 #pragma unroll
                     for (int a = 0; a < NV; a++) {
                         double s = Kh[a][j];
 #pragma unroll
-                        for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * Kh[c][j];
-                        Kh[a][j] = s * Luu[a * (a + 1) / 2 + a];
-                        out.fa[(R::KH + a * NX + j) * LANES] = Kh[a][j];
+                        for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * kj[c];
+                        kj[a] = s * Luu[a * (a + 1) / 2 + a];
+                        Kh[a][j] = kj[a];
+                        out.fa[(R::KH + a * NX + j) * LANES] = kj[a];
                     }
                 }
                 // last column first: column j reads only columns <= j of the successor's P (see CarryB)
 #pragma unroll
                 for (int j = NX - 1; j >= 0; j--) {
+                    if (RICCATI_FENCES) NMPC_PHASE_FENCE();
                     double g[NX], cu[NV], cx[NX];
                     P_col_s(P, lin, NV + j, g);
                     apply_T(lin, g, cu, cx);
+                    double kcj[NV];
+#pragma unroll
+                    for (int a = 0; a < NV; a++) kcj[a] = Kh[a][j];
 #pragma unroll
                     for (int i = j; i < NX; i++) {
                         double s = cx[i];
 #pragma unroll
-                        for (int a = 0; a < NV; a++) s -= Kh[a][i] * Kh[a][j];
+                        for (int a = 0; a < NV; a++) s -= Kh[a][i] * kcj[a];
                         if (i == j) s += tb.dt * tb.W[k * NY + i] + o.reg_prim + (i >= 3 + NV ? Gam[i - 3] : 0.0);
                         Pn[pk(i, j) * PSTRIDE] = s;
                     }

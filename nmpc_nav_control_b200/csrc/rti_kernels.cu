@@ -143,7 +143,7 @@ __device__ __forceinline__ void ctl_store(const typename S::LaneCtl& c, double* 
 //   gate: number of lanes still iterating (act[it]); 0 -> the whole grid returns at once.
 //   cnt_out (B kernels): lanes that continue -> act[it+1].
 template <class M, int KIND>
-__global__ void __launch_bounds__(LANES * SW_TILES, (KIND == Rti<M>::SW_FDF ? NMPC_FDF_MINB : 8) / SW_TILES)
+__global__ void __launch_bounds__(LANES * SW_TILES, (KIND == Rti<M>::SW_FDF ? NMPC_FDF_MINB : NMPC_B_MINB) / SW_TILES)
 k_sweep(int B, int i0, int nchunk, int ldc, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
         double* __restrict__ ctl_d, int* __restrict__ ctl_i, const int* __restrict__ gate, int* __restrict__ cnt_out, int gate_min,
         int defer_fb)
