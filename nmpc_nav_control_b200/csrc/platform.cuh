@@ -57,11 +57,8 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 // the update half of a stage is streamed channel by channel, and compiler fences between the columns of the Riccati
 // congruence bound how far the loads of later columns are hoisted.  omni4: 3.5 KB -> 0.9 KB of spill stores per thread,
 // 6.95 -> 5.75 ms per launch of 65,536 instances; diff / tric are faster in the whole-stage formulation (profiles/README_r02_notes.txt)
-#ifndef NMPC_B_STREAM_MINNV
-#define NMPC_B_STREAM_MINNV 4
-#endif
-#ifndef NMPC_RICCATI_FENCE_MINNV
-#define NMPC_RICCATI_FENCE_MINNV 4
+#ifndef NMPC_B_LEAN_MINNV
+#define NMPC_B_LEAN_MINNV 4
 #endif
 
 constexpr int LANES = 32;     // instances per tile = lanes per warp

@@ -134,6 +134,26 @@ struct Lin {
     static constexpr int NC = 1 + 3 * NV;
     double E[3][NC];
     double av[NV], ar[NV], au[NV], ru[NV];
+    NMPC_HD double e(int i, int c) const { return E[i][c]; }
+    NMPC_HD double a_v(int c) const { return av[c]; }
+    NMPC_HD double a_r(int c) const { return ar[c]; }
+    NMPC_HD double a_u(int c) const { return au[c]; }
+    NMPC_HD double r_u(int c) const { return ru[c]; }
+};
+// the same view with only the per-instance rows of E in registers: the theta row (where it is a per-stage constant) and
+// the lag constants are read from the broadcast tables where they are used (one address per warp, L1 hits) - the
+// factorising sweep of omni4 has no registers to hold them
+template <int NV, int ER>
+struct LinLean {
+    static constexpr int NC = 1 + 3 * NV;
+    double E[ER][NC];
+    const double* thr;
+    const double* lti;
+    NMPC_HD double e(int i, int c) const { return i < ER ? E[i < ER ? i : 0][c] : thr[c]; }
+    NMPC_HD double a_v(int c) const { return lti[c]; }
+    NMPC_HD double a_r(int c) const { return lti[NV + c]; }
+    NMPC_HD double a_u(int c) const { return lti[2 * NV + c]; }
+    NMPC_HD double r_u(int c) const { return lti[3 * NV + c]; }
 };
 
 template <class M>
@@ -142,9 +162,12 @@ struct Rti {
     static constexpr int NC = 1 + 3 * NV, NB2 = 2 * NV, NPK = NX * (NX + 1) / 2, NLU = NV * (NV + 1) / 2;
     static constexpr int NCON = 2 * (NV + (NSTAGE - 1) * NB2 + NV);   // one-sided constraints
     static constexpr int PSTRIDE = NMPC_SCRATCH_STRIDE;               // element stride of the per-lane scratch column
-    static constexpr bool RICCATI_FENCES = NV >= NMPC_RICCATI_FENCE_MINNV;
+    static constexpr bool LEAN = NV >= NMPC_B_LEAN_MINNV;            // register economy of the factorising sweep (platform.cuh)
+    static constexpr bool RICCATI_FENCES = LEAN;
     using R = Rec<NV, M::THETA_ROW_LTI ? 2 : 3>;
     using L = Lin<NV>;
+    template <bool B_, class D_ = void> struct LinSel { using type = Lin<NV>; };
+    template <class D_> struct LinSel<true, D_> { using type = LinLean<NV, Rec<NV, M::THETA_ROW_LTI ? 2 : 3>::ER>; };
 
     NMPC_HD static constexpr int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
@@ -334,6 +357,15 @@ struct Rti {
     // ------------------------------------------------------------------------------------
     // structured products with [B A] of one stage
     // ------------------------------------------------------------------------------------
+    using LLean = LinLean<NV, R::ER>;
+    NMPC_HD static void load_lin(const double* lin, const double* lti, const double* thr, LLean& l)
+    {
+#pragma unroll
+        for (int i = 0; i < R::ER; i++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) l.E[i][c] = lin[(R::E + i * NC + c) * LANES];
+        l.thr = thr; l.lti = lti;
+    }
     NMPC_HD static void load_lin(const double* lin, const double* lti, const double* thr, L& l)
     {
 #pragma unroll
@@ -344,64 +376,67 @@ struct Rti {
         for (int c = 0; c < NV; c++) { l.av[c] = lti[c]; l.ar[c] = lti[NV + c]; l.au[c] = lti[2 * NV + c]; l.ru[c] = lti[3 * NV + c]; }
     }
     // [B A]' v  -> ou (NV), ox (NX)
-    NMPC_HD static void apply_T(const L& l, const double* v, double* ou, double* ox)
+    template <class LL>
+    NMPC_HD static void apply_T(const LL& l, const double* v, double* ou, double* ox)
     {
 #pragma unroll
         for (int c = 0; c < NV; c++)
-            ou[c] = l.E[0][1 + 2 * NV + c] * v[0] + l.E[1][1 + 2 * NV + c] * v[1] + l.E[2][1 + 2 * NV + c] * v[2]
-                  + l.au[c] * v[3 + c] + l.ru[c] * v[3 + NV + c];
+            ou[c] = l.e(0, 1 + 2 * NV + c) * v[0] + l.e(1, 1 + 2 * NV + c) * v[1] + l.e(2, 1 + 2 * NV + c) * v[2]
+                  + l.a_u(c) * v[3 + c] + l.r_u(c) * v[3 + NV + c];
         ox[0] = v[0]; ox[1] = v[1];
-        ox[2] = l.E[0][0] * v[0] + l.E[1][0] * v[1] + l.E[2][0] * v[2];
+        ox[2] = l.e(0, 0) * v[0] + l.e(1, 0) * v[1] + l.e(2, 0) * v[2];
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            ox[3 + c] = l.E[0][1 + c] * v[0] + l.E[1][1 + c] * v[1] + l.E[2][1 + c] * v[2] + l.av[c] * v[3 + c];
-            ox[3 + NV + c] = l.E[0][1 + NV + c] * v[0] + l.E[1][1 + NV + c] * v[1] + l.E[2][1 + NV + c] * v[2]
-                           + l.ar[c] * v[3 + c] + v[3 + NV + c];
+            ox[3 + c] = l.e(0, 1 + c) * v[0] + l.e(1, 1 + c) * v[1] + l.e(2, 1 + c) * v[2] + l.a_v(c) * v[3 + c];
+            ox[3 + NV + c] = l.e(0, 1 + NV + c) * v[0] + l.e(1, 1 + NV + c) * v[1] + l.e(2, 1 + NV + c) * v[2]
+                           + l.a_r(c) * v[3 + c] + v[3 + NV + c];
         }
     }
     // A x + B u -> xn
-    NMPC_HD static void apply(const L& l, const double* u, const double* x, double* xn)
+    template <class LL>
+    NMPC_HD static void apply(const LL& l, const double* u, const double* x, double* xn)
     {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            double a = (i < 2 ? x[i] : 0.0) + l.E[i][0] * x[2];
+            double a = (i < 2 ? x[i] : 0.0) + l.e(i, 0) * x[2];
 #pragma unroll
             for (int c = 0; c < NV; c++)
-                a += l.E[i][1 + c] * x[3 + c] + l.E[i][1 + NV + c] * x[3 + NV + c] + l.E[i][1 + 2 * NV + c] * u[c];
+                a += l.e(i, 1 + c) * x[3 + c] + l.e(i, 1 + NV + c) * x[3 + NV + c] + l.e(i, 1 + 2 * NV + c) * u[c];
             xn[i] = a;
         }
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            xn[3 + c] = l.av[c] * x[3 + c] + l.ar[c] * x[3 + NV + c] + l.au[c] * u[c];
-            xn[3 + NV + c] = x[3 + NV + c] + l.ru[c] * u[c];
+            xn[3 + c] = l.a_v(c) * x[3 + c] + l.a_r(c) * x[3 + NV + c] + l.a_u(c) * u[c];
+            xn[3 + NV + c] = x[3 + NV + c] + l.r_u(c) * u[c];
         }
     }
     // g = P * (column j of [B A]), j in z order [u; x]
-    NMPC_HD static void P_col(const double* P, const L& l, int j, double* g)
+    template <class LL>
+    NMPC_HD static void P_col(const double* P, const LL& l, int j, double* g)
     {
         if (j < NV) {
             const int c = j;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = P[pk(i, 0)] * l.E[0][1 + 2 * NV + c] + P[pk(i, 1)] * l.E[1][1 + 2 * NV + c] + P[pk(i, 2)] * l.E[2][1 + 2 * NV + c]
-                     + P[pk(i, 3 + c)] * l.au[c] + P[pk(i, 3 + NV + c)] * l.ru[c];
+                g[i] = P[pk(i, 0)] * l.e(0, 1 + 2 * NV + c) + P[pk(i, 1)] * l.e(1, 1 + 2 * NV + c) + P[pk(i, 2)] * l.e(2, 1 + 2 * NV + c)
+                     + P[pk(i, 3 + c)] * l.a_u(c) + P[pk(i, 3 + NV + c)] * l.r_u(c);
         } else if (j < NV + 2) {
 #pragma unroll
             for (int i = 0; i < NX; i++) g[i] = P[pk(i, j - NV)];
         } else if (j == NV + 2) {
 #pragma unroll
-            for (int i = 0; i < NX; i++) g[i] = P[pk(i, 0)] * l.E[0][0] + P[pk(i, 1)] * l.E[1][0] + P[pk(i, 2)] * l.E[2][0];
+            for (int i = 0; i < NX; i++) g[i] = P[pk(i, 0)] * l.e(0, 0) + P[pk(i, 1)] * l.e(1, 0) + P[pk(i, 2)] * l.e(2, 0);
         } else if (j < NV + 3 + NV) {
             const int c = j - NV - 3;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = P[pk(i, 0)] * l.E[0][1 + c] + P[pk(i, 1)] * l.E[1][1 + c] + P[pk(i, 2)] * l.E[2][1 + c] + P[pk(i, 3 + c)] * l.av[c];
+                g[i] = P[pk(i, 0)] * l.e(0, 1 + c) + P[pk(i, 1)] * l.e(1, 1 + c) + P[pk(i, 2)] * l.e(2, 1 + c) + P[pk(i, 3 + c)] * l.a_v(c);
         } else {
             const int c = j - NV - 3 - NV;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = P[pk(i, 0)] * l.E[0][1 + NV + c] + P[pk(i, 1)] * l.E[1][1 + NV + c] + P[pk(i, 2)] * l.E[2][1 + NV + c]
-                     + P[pk(i, 3 + c)] * l.ar[c] + P[pk(i, 3 + NV + c)];
+                g[i] = P[pk(i, 0)] * l.e(0, 1 + NV + c) + P[pk(i, 1)] * l.e(1, 1 + NV + c) + P[pk(i, 2)] * l.e(2, 1 + NV + c)
+                     + P[pk(i, 3 + c)] * l.a_r(c) + P[pk(i, 3 + NV + c)];
         }
     }
 
@@ -456,32 +491,33 @@ struct Rti {
         }
     };
     // g = P * (column j of [B A]), P read from the scratch column
-    NMPC_HD static void P_col_s(const double* P, const L& l, int j, double* g)
+    template <class LL>
+    NMPC_HD static void P_col_s(const double* P, const LL& l, int j, double* g)
     {
 #define PP(i, m) P[pk(i, m) * PSTRIDE]
         if (j < NV) {
             const int c = j;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = PP(i, 0) * l.E[0][1 + 2 * NV + c] + PP(i, 1) * l.E[1][1 + 2 * NV + c] + PP(i, 2) * l.E[2][1 + 2 * NV + c]
-                     + PP(i, 3 + c) * l.au[c] + PP(i, 3 + NV + c) * l.ru[c];
+                g[i] = PP(i, 0) * l.e(0, 1 + 2 * NV + c) + PP(i, 1) * l.e(1, 1 + 2 * NV + c) + PP(i, 2) * l.e(2, 1 + 2 * NV + c)
+                     + PP(i, 3 + c) * l.a_u(c) + PP(i, 3 + NV + c) * l.r_u(c);
         } else if (j < NV + 2) {
 #pragma unroll
             for (int i = 0; i < NX; i++) g[i] = PP(i, j - NV);
         } else if (j == NV + 2) {
 #pragma unroll
-            for (int i = 0; i < NX; i++) g[i] = PP(i, 0) * l.E[0][0] + PP(i, 1) * l.E[1][0] + PP(i, 2) * l.E[2][0];
+            for (int i = 0; i < NX; i++) g[i] = PP(i, 0) * l.e(0, 0) + PP(i, 1) * l.e(1, 0) + PP(i, 2) * l.e(2, 0);
         } else if (j < NV + 3 + NV) {
             const int c = j - NV - 3;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = PP(i, 0) * l.E[0][1 + c] + PP(i, 1) * l.E[1][1 + c] + PP(i, 2) * l.E[2][1 + c] + PP(i, 3 + c) * l.av[c];
+                g[i] = PP(i, 0) * l.e(0, 1 + c) + PP(i, 1) * l.e(1, 1 + c) + PP(i, 2) * l.e(2, 1 + c) + PP(i, 3 + c) * l.a_v(c);
         } else {
             const int c = j - NV - 3 - NV;
 #pragma unroll
             for (int i = 0; i < NX; i++)
-                g[i] = PP(i, 0) * l.E[0][1 + NV + c] + PP(i, 1) * l.E[1][1 + NV + c] + PP(i, 2) * l.E[2][1 + NV + c]
-                     + PP(i, 3 + c) * l.ar[c] + PP(i, 3 + NV + c);
+                g[i] = PP(i, 0) * l.e(0, 1 + NV + c) + PP(i, 1) * l.e(1, 1 + NV + c) + PP(i, 2) * l.e(2, 1 + NV + c)
+                     + PP(i, 3 + c) * l.a_r(c) + PP(i, 3 + NV + c);
         }
 #undef PP
     }
@@ -882,7 +918,7 @@ struct Rti {
                                        const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
                                        double* gu, double* gx, double* rb, double* Gam)
     {
-        if (NV >= NMPC_B_STREAM_MINNV) stage_B_update_streamed(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
+        if (LEAN) stage_B_update_streamed(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
         else stage_B_update_whole(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
     }
 
@@ -897,7 +933,7 @@ struct Rti {
         const double* P = sc + (size_t)C::SC_P * PSTRIDE;         // successor's cost-to-go ...
         double* Pn = sc + (size_t)C::SC_P * PSTRIDE;              // ... overwritten in place by this stage's
         if (hasU) {
-            L lin;
+            typename LinSel<LEAN>::type lin;
             load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
 #pragma unroll
             for (int i = 0; i < NX; i++) out.fa[(R::RB + i) * LANES] = rb[i];
@@ -915,7 +951,10 @@ struct Rti {
 #pragma unroll
                 for (int c = 0; c < NV; c++) gu[c] += tu_[c];
 #pragma unroll
-                for (int j = 0; j < NX; j++) gx[j] += tx_[j];
+                for (int j = 0; j < NX; j++) {
+                    gx[j] += tx_[j];
+                    if (LEAN) sc[(C::SC_PV + j) * PSTRIDE] = gx[j];      // the successor's gradient is consumed: park this stage's in its slot
+                }
             }
             // M = [B A]' P [B A] + diag(H + Gamma + reg), built column by column in z order [u; x].
             // Control columns first: Muu (packed lower) and Mxu, then the Cholesky of Muu; the state
@@ -998,7 +1037,7 @@ struct Rti {
                 }
 #pragma unroll
                 for (int i = 0; i < NX; i++) {
-                    double s = gx[i];
+                    double s = LEAN ? sc[(C::SC_PV + i) * PSTRIDE] : gx[i];
 #pragma unroll
                     for (int a = 0; a < NV; a++) s -= Kh[a][i] * lh[a];
                     sc[(C::SC_PV + i) * PSTRIDE] = s;
