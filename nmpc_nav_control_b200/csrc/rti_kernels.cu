@@ -19,6 +19,7 @@
 
 #include "rti_core.cuh"
 #include "rti_coop.cuh"
+#include "rti_solo.cuh"
 #include "ctrl_glue.cuh"
 #include "path_disc.cuh"
 #include "rollout.cuh"
@@ -250,6 +251,35 @@ k_ipm_coop(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldW
     typename GP::Lane L;
     GP::init_lane(L, threadIdx.x & 31, threadIdx.x >> 5);
     GP::run_warp(&L, grp_sm, ws, i0, n, next, tb, We_inst, ldWe, o, out, rs);
+}
+
+// K3, block-per-instance mapping (rti_solo.cuh): the interior point of ONE instance in the shared memory of one SM - the
+// latency path (the ROS drop-in at batch 1, small fleets).  Reads the QP from the tile layout K1 / K2 wrote, leaves the QP
+// solution in IT.Z of the tile for K4.
+template <class M>
+__global__ void __launch_bounds__(Solo<M>::THREADS, 1)
+k_ipm_solo(int B, int i0, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
+           int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats)
+{
+    using S = Rti<M>;
+    using R = typename S::R;
+    static_assert(Solo<M>::THREADS > NSTAGE, "one thread per stage");
+    static_assert(Solo<M>::SM_BYTES <= 227 * 1024, "the interior-point state of one instance must fit the shared memory of an SM");
+    extern __shared__ __align__(16) double solo_sm[];
+    const int li = blockIdx.x, i = i0 + li;
+    double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
+    const double* We = We_inst ? We_inst + i : tb.We;
+    typename S::LaneStats st;
+    Solo<M>::run(solo_sm, tile_lane, tb, We, We_inst ? (size_t)B : 1, o, &st);
+    if (threadIdx.x == 0) {
+        qp_status[i] = st.status; qp_iter[i] = st.iter;
+        if (stats) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) stats[(size_t)q * B + i] = st.res[q];
+            stats[(size_t)4 * B + i] = st.mu; stats[(size_t)5 * B + i] = st.lin_res;
+            stats[(size_t)6 * B + i] = (double)st.cond_fallbacks; stats[(size_t)7 * B + i] = (double)st.status;
+        }
+    }
 }
 
 // K4 from the group layout
@@ -693,7 +723,9 @@ struct nmpc_solver {
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
-    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false;
+    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false, solo_attr_set = false;
+    int solo_max = -1;           // batches up to this size go to the block-per-instance kernel (diff, tric; 0: never; -1: four blocks per SM,
+                                 // where the lane-cooperative kernel catches up: 592 instances 4.0 ms against 4.7 ms on B200)
     size_t ws_doubles_per_inst = 0;
     ModelInfo mi;
     nmpc_ipm_opts opts;
@@ -806,6 +838,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     s->chunk = chunk < cap_pad ? chunk : cap_pad;
     s->tile_doubles = tile_doubles_of(model);
     if (const char* e = getenv("NMPC_K3")) s->k3_group = !strcmp(e, "sweep") ? 0 : !strcmp(e, "group") ? 1 : 2;
+    if (const char* e = getenv("NMPC_SOLO_MAX")) { int v = atoi(e); if (v >= 0) s->solo_max = v; }
     if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
     if (const char* e = getenv("NMPC_HYB_MIN")) { int v = atoi(e); if (v >= 0) s->hyb_min = v; }
     if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
@@ -814,6 +847,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     }
     cudaError_t e;
 #define CKC(call) do { e = (call); if (e != cudaSuccess) { set_err(NMPC_E_CUDA, #call, e); nmpc_destroy(s); return NMPC_E_CUDA; } } while (0)
+    if (s->solo_max < 0) { int nsm = 0; CKC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device)); s->solo_max = 4 * nsm; }
     CKC(cudaMalloc(&s->d_tab, s->tab_doubles * sizeof(double)));
     CKC(cudaMalloc(&s->d_x, (size_t)max_batch * (n + 1) * nx * sizeof(double)));
     CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
@@ -1099,6 +1133,53 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
 }
 
 
+#if defined(NMPC_SOLO_PROF)
+// phase cycles of block 0 of the block-per-instance kernel since the last call (experiment builds only)
+extern "C" int nmpc_solo_prof(unsigned long long* out)
+{
+    CK(cudaMemcpyFromSymbol(out, g_solo_prof, SOLO_NPROF * sizeof(unsigned long long)));
+    unsigned long long z[SOLO_NPROF] = {0};
+    CK(cudaMemcpyToSymbol(g_solo_prof, z, sizeof(z)));
+    return 0;
+}
+#endif
+
+// block-per-instance schedule (rti_solo.cuh): K1 / K2 into the tile layout, one block per instance, K4 from the tiles
+template <class M>
+static int solve_device_solo(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref, const double* d_We,
+                             double* d_x, double* d_u, int ld, int* d_status, int* d_qp_iter, double* d_stats, cudaStream_t st)
+{
+    using SO = Solo<M>;
+    const Tables tb = make_tables(s);
+    const IpmOpts o = to_core_opts(s->opts);
+    const int nchunks = (B + s->chunk - 1) / s->chunk;
+    int rc = ensure_events(s, nchunks);
+    if (rc) return rc;
+    s->last_chunks = nchunks; s->last_launches = 0;
+    if (!s->solo_attr_set) {
+        CK(cudaFuncSetAttribute(k_ipm_solo<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SO::SM_BYTES));
+        s->solo_attr_set = true;
+    }
+    k_fill_int<<<(B + 255) / 256, 256, 0, st>>>(B, d_status, 0);
+    s->last_launches++;
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * s->chunk;
+        const int n = (B - i0) < s->chunk ? (B - i0) : s->chunk;
+        cudaEvent_t* ev = &s->ev[(size_t)c * 4];
+        CK(cudaEventRecord(ev[0], st));
+        dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
+        k_linearize<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
+        CK(cudaEventRecord(ev[1], st));
+        k_ipm_solo<M><<<n, SO::THREADS, SO::SM_BYTES, st>>>(B, i0, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
+        CK(cudaEventRecord(ev[2], st));
+        k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
+        CK(cudaEventRecord(ev[3], st));
+        s->last_launches += 3;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // d_active / d_stepn (SQP passes, else null): only the instances with a non-zero flag are linearised, solved (through a
 // compacted queue) and stepped; the inf-norm of their step is accumulated into d_stepn
 template <class M>
@@ -1169,7 +1250,11 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
     if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
     if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
     CK(cudaEventRecord(s->ev_total[0], st));
-    if (s->k3_group == 1 || (s->k3_group == 2 && B < s->hyb_min)) {
+    if (s->k3_group == 2 && B <= s->solo_max && s->model != 1 && s->d_ws) {
+        // latency path: one block per instance (the omni4 state does not fit the shared memory of one SM)
+        if (s->model == 0) rc = solve_device_solo<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st);
+        else rc = solve_device_solo<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st);
+    } else if (s->k3_group == 1 || (s->k3_group == 2 && B < s->hyb_min)) {
         switch (s->model) {
             case 0: rc = solve_device_group<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;
             case 1: rc = solve_device_group<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st); break;

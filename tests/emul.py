@@ -39,7 +39,7 @@ def default_opts():
     return o
 
 
-def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, hybrid=None, coop=False):
+def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, hybrid=None, coop=False, solo=False):
     """one RTI step of B instances through the emulated kernel logic; returns dict like the oracle helper.
     coop = False: the per-lane K3 of rti_core.cuh (the lockstep sweeps); coop = True: the persistent lane-cooperative K3 of
     rti_coop.cuh (G = 4 nv lanes per instance); hybrid = K: K iterations of the per-lane sweeps, then hand-over of the
@@ -60,6 +60,8 @@ def emul_rti(name, x0, yref, x=None, u=None, We=None, tables=None, opts=None, hy
     fn, lead = (lib.emul_rti_coop, (C.c_int(0),)) if coop else (lib.emul_rti, ())
     if hybrid is not None:
         fn, lead = lib.emul_rti_hybrid, (C.c_int(hybrid),)
+    if solo:          # the block-per-instance mapping of rti_solo.cuh
+        fn, lead = lib.emul_rti_solo, ()
     rc = fn(C.c_int(spec.model_id), *lead, C.c_int(B), _dp(arrs["W"]), _dp(arrs["We"]), _dp(arrs["lbx"]), _dp(arrs["ubx"]),
                       _dp(arrs["lbu"]), _dp(arrs["ubu"]), _dp(arrs["p"]), C.c_double(tb["dt"]), C.byref(o),
                       _dp(x0), _dp(yref), C.c_int(nyref), None if we is None else _dp(we), _dp(x), _dp(u),

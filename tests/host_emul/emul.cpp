@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include "../../nmpc_nav_control_b200/csrc/rti_core.cuh"
 #include "../../nmpc_nav_control_b200/csrc/rti_coop.cuh"
+#include "../../nmpc_nav_control_b200/csrc/rti_solo.cuh"
 
 using namespace nmpc;
 
@@ -14,7 +15,7 @@ template <class M>
 static int run(int B, const double* W, const double* We, const double* lbx, const double* ubx,
                const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
                const double* x0bar, const double* yref, int nyref, const double* We_inst,
-               double* x, double* u, int* status, int* iters, double* stats)
+               double* x, double* u, int* status, int* iters, double* stats, bool solo = false)
 {
     using S = Rti<M>;
     using R = typename S::R;
@@ -40,7 +41,12 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
                                yi + k * nyref, nyref, x0bar + (size_t)i * NX, tb, wei,
                                base + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES, base + R::OFF_IT + (size_t)k * R::NF_IT * LANES);
         typename S::LaneStats st;
-        S::qp_ipm_lane(base, tb, wei, *o, st);
+        if (solo) {
+            // the block-per-instance mapping (rti_solo.cuh) run by one "thread": its phases execute item by item
+            std::vector<double> sm(Solo<M>::SM_DOUBLES, 0.0);
+            Solo<M>::run(sm.data(), base, tb, wei, 1, *o, &st);
+        } else
+            S::qp_ipm_lane(base, tb, wei, *o, st);
         status[i] = st.status; iters[i] = st.iter;
         if (stats) { for (int q = 0; q < 4; q++) stats[i * 8 + q] = st.res[q]; stats[i * 8 + 4] = st.mu; stats[i * 8 + 5] = st.lin_res; stats[i * 8 + 6] = st.cond_fallbacks; }
         if (st.status == 0 || st.status == 1)
@@ -59,6 +65,19 @@ extern "C" int emul_rti(int model, int B, const double* W, const double* We, con
         case 0: return run<DiffModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
         case 1: return run<Omni4Model>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
         case 2: return run<TricModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats);
+    }
+    return -1;
+}
+
+extern "C" int emul_rti_solo(int model, int B, const double* W, const double* We, const double* lbx, const double* ubx,
+                             const double* lbu, const double* ubu, const double* p, double dt, const IpmOpts* o,
+                             const double* x0bar, const double* yref, int nyref, const double* We_inst,
+                             double* x, double* u, int* status, int* iters, double* stats)
+{
+    switch (model) {
+        case 0: return run<DiffModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats, true);
+        case 1: return run<Omni4Model>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats, true);
+        case 2: return run<TricModel>(B, W, We, lbx, ubx, lbu, ubu, p, dt, o, x0bar, yref, nyref, We_inst, x, u, status, iters, stats, true);
     }
     return -1;
 }

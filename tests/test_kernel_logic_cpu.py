@@ -11,11 +11,11 @@ import emul
 from helpers import instances, oracle_solve, parity_report
 
 
-KINDS = ["coop", "lane"]
+KINDS = ["coop", "lane", "solo"]
 
 
 def _emul(name, x0, yref, kind, **kw):
-    return emul.emul_rti(name, x0, yref, coop=(kind == "coop"), **kw)
+    return emul.emul_rti(name, x0, yref, coop=(kind == "coop"), solo=(kind == "solo"), **kw)
 
 
 @pytest.mark.parametrize("kind", KINDS)
