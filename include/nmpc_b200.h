@@ -95,7 +95,13 @@ int nmpc_get_iterate_host(nmpc_solver* s, int B, double* x, double* u);
  *   d_status [B] (int)         acados status per instance
  *   d_qp_iter [B] (int)        interior-point iterations per instance
  *   d_stats [8][B] or NULL     res_g,res_b,res_d,res_m, mu, lin_res, cond_fallbacks, qp_status
- * Asynchronous on `stream` (cudaStream_t; NULL = the default stream); no host synchronisation inside. */
+ * Asynchronous on `stream` (cudaStream_t; NULL = the default stream); no host synchronisation inside.
+ * Which kernels run is chosen from the batch size (same results to rounding, same iteration counts):
+ *   B <= 4 x SMs (diff, tric)   one thread block per instance, state in shared memory - the latency path (batch 1: 0.7 ms)
+ *   B <  24,576                 the persistent lane-cooperative kernel
+ *   larger                      hybrid: lockstep per-lane sweeps, then the lane-cooperative kernel for the stragglers
+ * Environment overrides read at nmpc_create, for experiments: NMPC_K3 = sweep | group | hybrid, NMPC_SOLO_MAX = <largest batch
+ * of the block-per-instance kernel, 0 = never>, NMPC_HYB_MIN, NMPC_HYB_FRAC, NMPC_HYB_KMAX, NMPC_CHUNK. */
 int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const double* d_yref, int nyref,
                           const double* d_We, double* d_x, double* d_u, int ldxu,
                           int* d_status, int* d_qp_iter, double* d_stats, void* stream);
