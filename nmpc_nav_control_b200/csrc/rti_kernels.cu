@@ -259,7 +259,7 @@ k_ipm_coop(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldW
 template <class M>
 __global__ void __launch_bounds__(Solo<M>::THREADS, 1)
 k_ipm_solo(int B, int i0, Tables tb, const double* __restrict__ We_inst, IpmOpts o, double* __restrict__ ws,
-           int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats)
+           int* __restrict__ qp_status, int* __restrict__ qp_iter, double* __restrict__ stats, double* __restrict__ scr)
 {
     using S = Rti<M>;
     using R = typename S::R;
@@ -270,7 +270,8 @@ k_ipm_solo(int B, int i0, Tables tb, const double* __restrict__ We_inst, IpmOpts
     double* tile_lane = ws + (size_t)(li / LANES) * R::tile_doubles + (li % LANES);
     const double* We = We_inst ? We_inst + i : tb.We;
     typename S::LaneStats st;
-    Solo<M>::run(solo_sm, tile_lane, tb, We, We_inst ? (size_t)B : 1, o, &st);
+    Solo<M>::run(solo_sm, typename Solo<M>::TileIO{tile_lane}, tb, We, We_inst ? (size_t)B : 1, o, &st,
+                 scr ? scr + (size_t)blockIdx.x * Solo<M>::GSCR_DOUBLES : nullptr);
     if (threadIdx.x == 0) {
         qp_status[i] = st.status; qp_iter[i] = st.iter;
         if (stats) {
@@ -278,6 +279,35 @@ k_ipm_solo(int B, int i0, Tables tb, const double* __restrict__ We_inst, IpmOpts
             for (int q = 0; q < 4; q++) stats[(size_t)q * B + i] = st.res[q];
             stats[(size_t)4 * B + i] = st.mu; stats[(size_t)5 * B + i] = st.lin_res;
             stats[(size_t)6 * B + i] = (double)st.cond_fallbacks; stats[(size_t)7 * B + i] = (double)st.status;
+        }
+    }
+}
+
+// the same on the per-instance records of the lane-cooperative path (k_linearize_g / k_step_g around it): block b takes entry b
+// of the queue (all n instances of the chunk, or the compacted list of the instances an SQP pass still iterates)
+template <class M>
+__global__ void __launch_bounds__(Solo<M>::THREADS, 1)
+k_ipm_solo_g(int i0, int n, Tables tb, const double* __restrict__ We_inst, int ldWe, IpmOpts o, double* __restrict__ ws,
+             GrpOut out, GrpResume rs, double* __restrict__ scr)
+{
+    using S = Rti<M>;
+    using GR = GRec<S::NV>;
+    extern __shared__ __align__(16) double solo_sm[];
+    const int cnt = rs.n_dev ? *rs.n_dev : n;
+    if ((int)blockIdx.x >= cnt) return;
+    const int gi = rs.list ? rs.list[blockIdx.x] : (int)blockIdx.x;
+    const int i = i0 + gi;
+    const double* We = We_inst ? We_inst + i : tb.We;
+    typename S::LaneStats st;
+    Solo<M>::run(solo_sm, typename Solo<M>::RecIO{ws + (size_t)gi * GR::inst_doubles}, tb, We, We_inst ? (size_t)ldWe : 1, o, &st,
+                 scr ? scr + (size_t)blockIdx.x * Solo<M>::GSCR_DOUBLES : nullptr);
+    if (threadIdx.x == 0) {
+        out.qp_status[i] = st.status; out.qp_iter[i] = st.iter;
+        if (out.stats) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) out.stats[(size_t)q * out.B + i] = st.res[q];
+            out.stats[(size_t)4 * out.B + i] = st.mu; out.stats[(size_t)5 * out.B + i] = st.lin_res;
+            out.stats[(size_t)6 * out.B + i] = (double)st.cond_fallbacks; out.stats[(size_t)7 * out.B + i] = (double)st.status;
         }
     }
 }
@@ -716,6 +746,7 @@ struct nmpc_solver {
     int k3_group = 2;            // K3 schedule: 0 per-sweep kernels (rti_core.cuh), 1 persistent lane-cooperative kernel (rti_coop.cuh),
                                  // 2 hybrid: per-sweep kernels while most instances iterate, then the group kernel for the rest
     double *d_ws_g = nullptr;    // group workspace (schedules 1, 2)
+    double *d_solo_scr = nullptr; // block-per-instance kernel, models whose state exceeds the shared memory of an SM (omni4): [B A], Phi, Phi' per instance
     int *d_list = nullptr, *d_map = nullptr;
     void* d_ctl_g = nullptr;
     int hyb_kmax = 12; double hyb_frac = 0.75;  // hand over once fewer than 75 % of the chunk iterate: a lockstep launch costs the same at any
@@ -723,7 +754,7 @@ struct nmpc_solver {
     int hyb_min = 24576;         // smaller batches go to the group kernel alone (its per-iteration latency is 3-4x lower)
     int grp_blocks = 0;
     // function attributes (dynamic shared memory opt-in) are per device: remembered per solver, not per process
-    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false, solo_attr_set = false;
+    int grp_blocks_per_sm = 0; bool sweep_attr_set = false, lin_attr_set = false, solo_attr_set = false, solo_g_attr_set = false;
     int solo_max = -1;           // batches up to this size go to the block-per-instance kernel (diff, tric; 0: never; -1: four blocks per SM,
                                  // where the lane-cooperative kernel catches up: 592 instances 4.0 ms against 4.7 ms on B200)
     size_t ws_doubles_per_inst = 0;
@@ -847,7 +878,10 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     }
     cudaError_t e;
 #define CKC(call) do { e = (call); if (e != cudaSuccess) { set_err(NMPC_E_CUDA, #call, e); nmpc_destroy(s); return NMPC_E_CUDA; } } while (0)
-    if (s->solo_max < 0) { int nsm = 0; CKC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device)); s->solo_max = 4 * nsm; }
+    if (s->solo_max < 0) { int nsm = 0; CKC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device)); s->solo_max = (model == 1 ? 2 : 4) * nsm; }
+    if (s->solo_max > max_batch) s->solo_max = max_batch;
+    if (model == 1 && s->k3_group == 2 && s->solo_max > 0)
+        CKC(cudaMalloc(&s->d_solo_scr, (size_t)s->solo_max * Solo<Omni4Model>::GSCR_DOUBLES * sizeof(double)));
     CKC(cudaMalloc(&s->d_tab, s->tab_doubles * sizeof(double)));
     CKC(cudaMalloc(&s->d_x, (size_t)max_batch * (n + 1) * nx * sizeof(double)));
     CKC(cudaMalloc(&s->d_u, (size_t)max_batch * n * nu * sizeof(double)));
@@ -885,7 +919,7 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
     cudaSetDevice(s->device);
     cudaFree(s->d_vref); cudaFree(s->d_cin); cudaFree(s->d_cnref); cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
     cudaFree(s->d_ctl_d); cudaFree(s->d_ctl_i); cudaFree(s->d_cnt);
-    cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
+    cudaFree(s->d_solo_scr); cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
     cudaFree(s->d_status); cudaFree(s->d_iter); cudaFree(s->d_stats);
     cudaFree(s->d_sqp_active); cudaFree(s->d_sqp_iter); cudaFree(s->d_sqp_qp); cudaFree(s->d_sqp_stepn);
@@ -1170,7 +1204,7 @@ static int solve_device_solo(nmpc_solver* s, int B, const double* d_x0bar, const
         dim3 g1((n + LIN_BLOCK - 1) / LIN_BLOCK, NSTAGE + 1);
         k_linearize<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ld, tb, s->d_ws);
         CK(cudaEventRecord(ev[1], st));
-        k_ipm_solo<M><<<n, SO::THREADS, SO::SM_BYTES, st>>>(B, i0, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats);
+        k_ipm_solo<M><<<n, SO::THREADS, SO::SM_BYTES, st>>>(B, i0, tb, d_We, o, s->d_ws, s->d_qp_status, d_qp_iter, d_stats, s->d_solo_scr);
         CK(cudaEventRecord(ev[2], st));
         k_step<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws, s->d_qp_status, d_status);
         CK(cudaEventRecord(ev[3], st));
@@ -1222,8 +1256,23 @@ static int solve_device_group(nmpc_solver* s, int B, const double* d_x0bar, cons
             rs = GrpResume{cnt, s->d_list, nullptr};
             s->last_launches++;
         }
-        rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, rs, st);
-        if (rc) return rc;
+        bool solo = false;
+        {
+            // small batches (the SQP passes of a small fleet): one block per queued instance (rti_solo.cuh)
+            if (s->k3_group == 2 && n <= s->solo_max) {
+                using SO = Solo<M>;
+                if (!s->solo_g_attr_set) {
+                    CK(cudaFuncSetAttribute(k_ipm_solo_g<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SO::SM_BYTES));
+                    s->solo_g_attr_set = true;
+                }
+                k_ipm_solo_g<M><<<n, SO::THREADS, SO::SM_BYTES, st>>>(i0, n, tb, d_We, B, o, s->d_ws_g, out, rs, s->d_solo_scr);
+                solo = true;
+            }
+        }
+        if (!solo) {
+            rc = launch_group_any<M>(s, i0, n, tb, d_We, B, o, out, rs, st);
+            if (rc) return rc;
+        }
         CK(cudaEventRecord(ev[2], st));
         k_step_g<M><<<g1, LIN_BLOCK, 0, st>>>(B, i0, n, d_x0bar, d_x, d_u, ld, s->d_ws_g, s->d_qp_status, d_status, d_active, d_stepn);
         CK(cudaEventRecord(ev[3], st));
@@ -1250,9 +1299,10 @@ extern "C" int nmpc_rti_solve_device(nmpc_solver* s, int B, const double* d_x0ba
     if (!d_x) { d_x = s->d_x; d_u = s->d_u; ldxu = s->cap; }
     if (ldxu < B) return set_err(NMPC_E_ARG, "nmpc_rti_solve_device: leading dimension < B");
     CK(cudaEventRecord(s->ev_total[0], st));
-    if (s->k3_group == 2 && B <= s->solo_max && s->model != 1 && s->d_ws) {
-        // latency path: one block per instance (the omni4 state does not fit the shared memory of one SM)
+    if (s->k3_group == 2 && B <= s->solo_max && s->d_ws) {
+        // latency path: one block per instance
         if (s->model == 0) rc = solve_device_solo<DiffModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st);
+        else if (s->model == 1) rc = solve_device_solo<Omni4Model>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st);
         else rc = solve_device_solo<TricModel>(s, B, d_x0bar, d_yref, nyref, d_We, d_x, d_u, ldxu, d_status, d_qp_iter, d_stats, st);
     } else if (s->k3_group == 1 || (s->k3_group == 2 && B < s->hyb_min)) {
         switch (s->model) {

@@ -26,7 +26,7 @@
 // what another item of the same phase writes, except where stated (neighbour reads are split off into a read block that
 // ends with a barrier).
 #pragma once
-#include "rti_core.cuh"
+#include "rti_records.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define SOLO_HOST 0
@@ -49,11 +49,11 @@
 __device__ unsigned long long g_solo_prof[SOLO_NPROF];
 #endif
 #if defined(__CUDA_ARCH__) && defined(NMPC_SOLO_PROF)
-#define SOLO_T(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long c_ = clock64(); long long* l_ = reinterpret_cast<long long*>(sm + O_SC + 1); \
+#define SOLO_T(id) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long c_ = clock64(); long long* l_ = reinterpret_cast<long long*>(sm + O_SC + 2); \
                         l_[1 + (id)] += c_ - l_[0]; l_[0] = c_; } } while (0)
-#define SOLO_T0() do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long* l_ = reinterpret_cast<long long*>(sm + O_SC + 1); l_[0] = clock64(); \
+#define SOLO_T0() do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long* l_ = reinterpret_cast<long long*>(sm + O_SC + 2); l_[0] = clock64(); \
                        for (int q_ = 0; q_ < SOLO_NPROF; q_++) l_[1 + q_] = 0; } } while (0)
-#define SOLO_TEND() do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long* l_ = reinterpret_cast<const long long*>(sm + O_SC + 1); \
+#define SOLO_TEND() do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long* l_ = reinterpret_cast<const long long*>(sm + O_SC + 2); \
                          for (int q_ = 0; q_ < SOLO_NPROF; q_++) g_solo_prof[q_] += (unsigned long long)l_[1 + q_]; } } while (0)
 #else
 #define SOLO_T(id) ((void)0)
@@ -74,8 +74,13 @@ struct Solo {
     static constexpr int THREADS = ((N + 1 + 31) / 32) * 32;      // one thread per stage, whole warps
 
     // ---- shared-memory block of one stage (doubles) --------------------------------------------------------------------
-    static constexpr int O_J = 0;                      // NX*NZ  dense [B A], row-major, columns in z order [u; x]
-    static constexpr int O_DLB = O_J + NX * NZ;        // NB2    lb - z for [u; ref]
+    // Models with more than two channels (omni4: 81 stages x 559 doubles = 362 KB) do not fit the shared memory of an SM: their
+    // two largest per-stage arrays, the dense [B A] and the closed-loop matrix with its transpose, live in a per-instance
+    // scratch area in global memory instead (L2 resident, 278 KB); the sequential loops fetch the next stage's rows into
+    // registers while they work on the current one.
+    static constexpr bool BIG = NV > 2;
+    static constexpr int O_J = 0;                      // NX*NZ  dense [B A], row-major, columns in z order [u; x]   (not BIG)
+    static constexpr int O_DLB = O_J + (BIG ? 0 : NX * NZ);   // NB2    lb - z for [u; ref]
     static constexpr int O_DUB = O_DLB + NB2;          // NB2
     static constexpr int O_Q = O_DUB + NB2;            // NZ     QP gradient
     static constexpr int O_B0 = O_Q + NZ;              // NX     phi(x,u) - x_next
@@ -100,8 +105,8 @@ struct Solo {
     //      for the forward passes, rows of the transpose for the backward ones) --------------------------------------------------
     static constexpr int NXP = (NX + 1) & ~1;
     static constexpr int R_PHI = 0;                    // NX*NXP closed-loop matrix A - B K, row-major
-    static constexpr int R_PHT = R_PHI + NX * NXP;     // NX*NXP its transpose
-    static constexpr int R_V = R_PHT + NX * NXP;       // NXP    running backward recursion (multiplier step / gradient / delta adjoint)
+    static constexpr int R_PHT = R_PHI + (BIG ? 0 : NX * NXP);     // NX*NXP its transpose
+    static constexpr int R_V = R_PHT + (BIG ? 0 : NX * NXP);       // NXP    running backward recursion (multiplier step / gradient / delta adjoint)
     static constexpr int R_X = R_V + NXP;              // NXP    running forward recursion (state step)
     static constexpr int R_C = R_X + NXP;              // NXP    constant term of the forward recursion
     static constexpr int RS0 = R_C + NXP;
@@ -116,10 +121,18 @@ struct Solo {
     static constexpr int O_CTL = O_LH + NV;            // LaneCtl
     static constexpr int CTL_D = (int)((sizeof(LaneCtl) + 7) / 8);
     static constexpr int O_SC = O_CTL + CTL_D;         // a_step
-    static constexpr int O_REC = (O_SC + 2 + SOLO_NPROF + 2 + 1) & ~1;
+    static constexpr int O_REC = (O_SC + 3 + SOLO_NPROF + 2 + 1) & ~1;
     static constexpr int SM_DOUBLES = O_REC + (N + 1) * RS;
     static_assert(O_P % 2 == 0 && O_REC % 2 == 0 && RS % 2 == 0 && NXP % 2 == 0, "16-byte loads of padded rows");
     NMPC_HD static double* rec(double* sm, int k) { return sm + O_REC + (size_t)k * RS; }
+    // per-instance global scratch of the BIG models: per stage [J | Phi | Phi']
+    static constexpr int JSZ = (NX * NZ + 1) & ~1;                // rows of Phi stay 16-byte aligned
+    static constexpr int GS = JSZ + 2 * NX * NXP;
+    static constexpr size_t GSCR_DOUBLES = BIG ? (size_t)(N + 1) * GS : 0;
+    NMPC_HD static double*& gscr(double* sm) { return *reinterpret_cast<double**>(sm + O_SC + 1); }
+    NMPC_HD static double* Jp(double* sm, int k) { return BIG ? gscr(sm) + (size_t)k * GS : sm + (size_t)k * PS + O_J; }
+    NMPC_HD static double* phi(double* sm, int k) { return BIG ? gscr(sm) + (size_t)k * GS + JSZ : rec(sm, k) + R_PHI; }
+    NMPC_HD static double* pht(double* sm, int k) { return BIG ? gscr(sm) + (size_t)k * GS + JSZ + NX * NXP : rec(sm, k) + R_PHT; }
     // s0 + row . v with the row in shared memory (16-byte aligned, padded) and v in registers
     NMPC_HD static double dotp_r(const double* row, const double (&v)[NX], double s0)
     {
@@ -182,21 +195,53 @@ struct Solo {
         }
     }
 
+    // ---- where the QP of the instance comes from and where its solution goes: the tile layout of the lockstep sweeps (K1 / K2 =
+    //      k_linearize, K4 = k_step) or the per-instance records of the lane-cooperative kernel (k_linearize_g, k_step_g; the SQP
+    //      passes with their active-instance queue) ---------------------------------------------------------------------------------
+    struct TileIO {
+        double* lane;                                   // lane-resolved base of the instance's tile
+        static constexpr int ER = R::ER;
+        NMPC_HD const double* lin(int k) const { return lane + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES; }
+        NMPC_HD double e(int k, int i, int c) const { return lin(k)[(R::E + i * NC + c) * LANES]; }
+        NMPC_HD double b0(int k, int i) const { return lin(k)[(R::B0 + i) * LANES]; }
+        NMPC_HD double dlb(int k, int b) const { return lin(k)[(R::DLB + b) * LANES]; }
+        NMPC_HD double dub(int k, int b) const { return lin(k)[(R::DUB + b) * LANES]; }
+        NMPC_HD double q(int k, int w) const { return lin(k)[(R::Q + w) * LANES]; }
+        NMPC_HD double z0(int j) const { return lane[R::OFF_IT + (R::Z + NU + j) * LANES]; }
+        NMPC_HD void put_z(int k, int w, double v) const { lane[R::OFF_IT + ((size_t)k * R::NF_IT + R::Z + w) * LANES] = v; }
+    };
+    struct RecIO {
+        using GR = GRec<NV>;
+        double* base;                                   // the instance's records, stage-major
+        static constexpr int ER = 3;
+        NMPC_HD double e(int k, int i, int c) const { return base[(size_t)k * GR::NREC + GR::E + i * NC + c]; }
+        NMPC_HD double b0(int k, int i) const { return base[(size_t)k * GR::NREC + GR::B0 + i]; }
+        NMPC_HD double dlb(int k, int b) const { return base[(size_t)k * GR::NREC + GR::DLB + b]; }
+        NMPC_HD double dub(int k, int b) const { return base[(size_t)k * GR::NREC + GR::DUB + b]; }
+        NMPC_HD double q(int k, int w) const { return base[(size_t)k * GR::NREC + GR::Q + w]; }
+        NMPC_HD double z0(int j) const { return base[GR::Z + NU + j]; }
+        NMPC_HD void put_z(int k, int w, double v) const { base[(size_t)k * GR::NREC + GR::Z + w] = v; }
+    };
+
     // ---- set-up: the QP of the instance from its tile (written by K1 / K2) into the stage blocks -----------------------------
-    NMPC_HD static void load_qp(double* sm, const double* tile_lane, const Tables& tb)
+    template <class IO>
+    NMPC_HD static void load_qp(double* sm, const IO& io, const Tables& tb)
     {
         for (int e = SOLO_TID; e < (N + 1) * RS; e += SOLO_NT) sm[O_REC + e] = 0.0;      // incl. the row padding
+        if (BIG) {
+            for (int e = SOLO_TID; e < (N + 1) * 2 * NX * NXP; e += SOLO_NT)
+                gscr(sm)[(size_t)(e / (2 * NX * NXP)) * GS + JSZ + e % (2 * NX * NXP)] = 0.0;
+        }
         for (int k = SOLO_TID; k <= N; k += SOLO_NT) {
             double* st = sm + (size_t)k * PS;
-            const double* lin = tile_lane + R::OFF_LIN + (size_t)k * R::NF_LIN * LANES;
             if (k < N) {
                 const double* lti = tb.lti + k * 4 * NV;
                 const double* thr = tb.thr + k * NC;
-                double* J = st + O_J;
+                double* J = Jp(sm, k);
                 for (int e = 0; e < NX * NZ; e++) J[e] = 0.0;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    auto E = [&](int c) { return i < R::ER ? lin[(R::E + i * NC + c) * LANES] : thr[c]; };
+                    auto E = [&](int c) { return i < IO::ER ? io.e(k, i, c) : thr[c]; };
                     if (i < 2) J[i * NZ + NU + i] = 1.0;
                     J[i * NZ + NU + 2] = E(0);
 #pragma unroll
@@ -215,20 +260,19 @@ struct Solo {
                     J[(3 + NV + c) * NZ + NU + 3 + NV + c] = 1.0;
                 }
 #pragma unroll
-                for (int i = 0; i < NX; i++) st[O_B0 + i] = lin[(R::B0 + i) * LANES];
+                for (int i = 0; i < NX; i++) st[O_B0 + i] = io.b0(k, i);
             }
 #pragma unroll
             for (int b = 0; b < NB2; b++) {
                 const bool act = (b < NV) ? (k < N) : (k > 0);
-                st[O_DLB + b] = act ? lin[(R::DLB + b) * LANES] : 0.0;
-                st[O_DUB + b] = act ? lin[(R::DUB + b) * LANES] : 0.0;
+                st[O_DLB + b] = act ? io.dlb(k, b) : 0.0;
+                st[O_DUB + b] = act ? io.dub(k, b) : 0.0;
             }
 #pragma unroll
-            for (int w = 0; w < NZ; w++) st[O_Q + w] = lin[(R::Q + w) * LANES];
+            for (int w = 0; w < NZ; w++) st[O_Q + w] = io.q(k, w);
             if (k == 0) {
-                const double* it = tile_lane + R::OFF_IT;
 #pragma unroll
-                for (int j = 0; j < NX; j++) st[O_Z + NU + j] = it[(R::Z + NU + j) * LANES];    // x0 elimination: the constant stage-0 state
+                for (int j = 0; j < NX; j++) st[O_Z + NU + j] = io.z0(j);    // x0 elimination: the constant stage-0 state
             }
         }
         SOLO_SYNC();
@@ -249,7 +293,7 @@ struct Solo {
                 c[j] = st[O_Q + NU + j] + H * st[O_Z + NU + j] - st[O_PI + j] + H * st[O_DZ + NU + j];
             }
             if (hasU) {
-                const double* J = st + O_J;
+                const double* J = Jp(sm, k);
                 const double* pio = st + PS + O_PI;
 #pragma unroll
                 for (int j = 0; j < NX; j++) {
@@ -304,7 +348,7 @@ struct Solo {
     {
 #if SOLO_HOST
         for (int k = N - 1; k >= 1; k--) {
-            const double* A = sm + (size_t)k * PS + O_J + NU;
+            const double* A = Jp(sm, k) + NU;
             double* rc = rec(sm, k);
             for (int j = 0; j < NX; j++) {
                 const double* vn = rc + RS + R_V;
@@ -320,7 +364,7 @@ struct Solo {
 #pragma unroll 2
         for (int k = N - 1; k >= 1; k--) {
             double* rc = rec(sm, k);
-            v = dot_shfl<NZ>(sm + (size_t)k * PS + O_J + NU + j, v, rc[R_V + j]);
+            v = dot_shfl<NZ>(Jp(sm, k) + NU + j, v, rc[R_V + j]);
             if (threadIdx.x < NX) rc[R_V + j] = v;
         }
 #endif
@@ -330,7 +374,7 @@ struct Solo {
 #if SOLO_HOST
         for (int k = N - 1; k >= 1; k--) {
             double* rc = rec(sm, k);
-            for (int j = 0; j < NX; j++) rc[R_V + j] = dotp(rc + R_PHT + j * NXP, rc + RS + R_V, rc[R_V + j]);
+            for (int j = 0; j < NX; j++) rc[R_V + j] = dotp(pht(sm, k) + j * NXP, rc + RS + R_V, rc[R_V + j]);
         }
 #else
         if (threadIdx.x >= 32) return;
@@ -339,7 +383,7 @@ struct Solo {
 #pragma unroll 2
         for (int k = N - 1; k >= 1; k--) {
             double* rc = rec(sm, k);
-            v = dot_shfl<1>(rc + R_PHT + j * NXP, v, rc[R_V + j]);
+            v = dot_shfl<1>(pht(sm, k) + j * NXP, v, rc[R_V + j]);
             if (threadIdx.x < NX) rc[R_V + j] = v;
         }
 #endif
@@ -350,7 +394,7 @@ struct Solo {
         for (int i = 0; i < NX; i++) { rec(sm, 0)[R_X + i] = 0.0; rec(sm, 1)[R_X + i] = rec(sm, 0)[R_C + i]; }
         for (int k = 1; k < N; k++) {
             double* rc = rec(sm, k);
-            for (int i = 0; i < NX; i++) rc[RS + R_X + i] = dotp(rc + R_PHI + i * NXP, rc + R_X, rc[R_C + i]);
+            for (int i = 0; i < NX; i++) rc[RS + R_X + i] = dotp(phi(sm, k) + i * NXP, rc + R_X, rc[R_C + i]);
         }
 #else
         if (threadIdx.x >= 32) return;
@@ -360,7 +404,7 @@ struct Solo {
 #pragma unroll 2
         for (int k = 1; k < N; k++) {
             double* rc = rec(sm, k);
-            x = dot_shfl<1>(rc + R_PHI + i * NXP, x, rc[R_C + i]);
+            x = dot_shfl<1>(phi(sm, k) + i * NXP, x, rc[R_C + i]);
             if (threadIdx.x < NX) rc[RS + R_X + i] = x;
         }
 #endif
@@ -391,7 +435,7 @@ struct Solo {
             const NbTmp& t = tmp[SOLO_HOST ? k : 0];
             double* st = sm + (size_t)k * PS;
             const bool hasU = k < N, hasX = k > 0;
-            const double* J = st + O_J;
+            const double* J = Jp(sm, k);
             double ng = 0.0, nb_ = 0.0, nd = 0.0, nm = 0.0, lru = 0.0, musum = 0.0;
             // bounded components: step in the slacks and multipliers, residuals and barrier terms at the new iterate
             double b_ldo[NB2], b_dld[NB2], b_lnew[NB2], b_gam[NB2], b_Gam[NB2], b_zn[NB2];
@@ -530,7 +574,7 @@ struct Solo {
         SOLO_SYNC();
         for (int k = N - 1; k >= 0; k--) {
             double* st = sm + (size_t)k * PS;
-            const double* J = st + O_J;
+            const double* J = Jp(sm, k);
             const bool hasX = k > 0;
             // ---- phase A
 #pragma unroll
@@ -627,7 +671,7 @@ struct Solo {
         SOLO_SYNC();
         for (int k = N - 1; k >= 0; k--) {
             double* st = sm + (size_t)k * PS;
-            const double* J = st + O_J;
+            const double* J = Jp(sm, k);
             const bool hasX = k > 0;
             // G = P [B A];  w = P rb + p_{k+1}
             for (int e = t; e < NX * NZ + NX; e += nt) {
@@ -751,7 +795,7 @@ struct Solo {
     {
         for (int k = SOLO_TID; k < N; k += SOLO_NT) {
             double* st = sm + (size_t)k * PS;
-            const double* J = st + O_J; const double* Luu = st + O_LUU;
+            const double* J = Jp(sm, k); const double* Luu = st + O_LUU;
             if (FAST) {
                 // the two-phase recursion left Muu (row-packed), S and g_u: factorise, K = Luu^-1 S, feed-forward control
                 double L[NLU];
@@ -808,7 +852,7 @@ struct Solo {
                     double s = J[i * NZ + NU + j];
 #pragma unroll
                     for (int a = 0; a < NV; a++) s -= J[i * NZ + a] * kf[a];
-                    rec(sm, k)[R_PHI + i * NXP + j] = s; rec(sm, k)[R_PHT + j * NXP + i] = s;
+                    phi(sm, k)[i * NXP + j] = s; pht(sm, k)[j * NXP + i] = s;
                 }
             }
 #pragma unroll
@@ -827,7 +871,7 @@ struct Solo {
     {
         for (int k = SOLO_TID; k < N; k += SOLO_NT) {
             double* st = sm + (size_t)k * PS;
-            const double* J = st + O_J;
+            const double* J = Jp(sm, k);
             const double* vn = rec(sm, k + 1) + R_V;
             double tv[NV], uf[NV];
 #pragma unroll
@@ -1032,13 +1076,16 @@ struct Solo {
         SOLO_T(15);
     }
 
-    // the whole interior-point solve of the instance whose tile lane is `tile_lane`; every thread of the block calls it.
-    // Leaves the QP solution in IT.Z of the tile (what K4 reads) and the statistics in `out` (thread 0).
-    NMPC_HD static void run(double* sm, double* tile_lane, const Tables& tb, const double* We, size_t wst, const IpmOpts& o,
-                            typename S::LaneStats* out)
+    // the whole interior-point solve of the instance behind `io`; every thread of the block calls it.
+    // Leaves the QP solution where K4 reads it (io.put_z) and the statistics in `out` (thread 0).
+    template <class IO>
+    NMPC_HD static void run(double* sm, const IO& io, const Tables& tb, const double* We, size_t wst, const IpmOpts& o,
+                            typename S::LaneStats* out, double* gscratch = nullptr)
     {
+        if (SOLO_TID == 0) gscr(sm) = gscratch;          // BIG models: GSCR_DOUBLES of global memory of this instance's own
+        SOLO_SYNC();
         SOLO_T0();
-        load_qp(sm, tile_lane, tb);
+        load_qp(sm, io, tb);
         if (SOLO_TID == 0) ctl(sm).init(true);
         SOLO_SYNC();
         SOLO_T(0);
@@ -1057,9 +1104,8 @@ struct Solo {
         }
         for (int k = SOLO_TID; k <= N; k += SOLO_NT) {
             const double* st = sm + (size_t)k * PS;
-            double* it = tile_lane + R::OFF_IT + (size_t)k * R::NF_IT * LANES;
 #pragma unroll
-            for (int w = 0; w < NZ; w++) it[(R::Z + w) * LANES] = st[O_Z + w];
+            for (int w = 0; w < NZ; w++) io.put_z(k, w, st[O_Z + w]);
         }
         SOLO_TEND();
         if (SOLO_TID == 0 && out) {

@@ -43,8 +43,8 @@ static int run(int B, const double* W, const double* We, const double* lbx, cons
         typename S::LaneStats st;
         if (solo) {
             // the block-per-instance mapping (rti_solo.cuh) run by one "thread": its phases execute item by item
-            std::vector<double> sm(Solo<M>::SM_DOUBLES, 0.0);
-            Solo<M>::run(sm.data(), base, tb, wei, 1, *o, &st);
+            std::vector<double> sm(Solo<M>::SM_DOUBLES, 0.0), gs(Solo<M>::GSCR_DOUBLES + 1, 0.0);
+            Solo<M>::run(sm.data(), typename Solo<M>::TileIO{base}, tb, wei, 1, *o, &st, gs.data());
         } else
             S::qp_ipm_lane(base, tb, wei, *o, st);
         status[i] = st.status; iters[i] = st.iter;

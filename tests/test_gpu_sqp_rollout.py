@@ -4,6 +4,8 @@ controller tick -> plant step -> shift enqueued by ONE call of the C ABI).  Not 
 RTI step per tick and never shifts: NMPCNavControlROS.cpp:309,316,326 -> NMPCNavControlDiff.cpp:142); the shapes mirrored are
 scripts/test_scripts/casadi_sim_diff.py:104-106 (warm start from the previous solution) and acados_sim_diff.py:119-163
 (closed loop).  Parity target: the oracle driven through the same protocol (oracle/ctrl.py, oracle/rollout.py)."""
+import time
+
 import numpy as np
 import pytest
 import torch
@@ -169,8 +171,10 @@ def test_config4_tric_200_ticks_sqp_shift_through_one_call():
         ro.x[3].fill_(0.3); ro.x[4].fill_(0.15); ro.x[5].fill_(0.3); ro.x[6].fill_(0.15)
         ro.vel[0].fill_(0.3); ro.steer.fill_(0.15)
         ctl.reference_states()[0, :B].fill_(0.3); ctl.reference_states()[1, :B].fill_(0.15)
+        t0 = time.perf_counter()
         r = ro.run_engine(T, None, sqp_max_iter=6, sqp_tol=1e-8, shift=True)
         torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
         outs.append({k: v.clone() for k, v in r.items()})
         assert int(r["failed"].sum()) == 0 and torch.isfinite(r["pose"]).all() and torch.isfinite(r["cmd"]).all()
     assert torch.equal(outs[0]["pose"], outs[1]["pose"]) and torch.equal(outs[0]["cmd"], outs[1]["cmd"])
@@ -185,5 +189,6 @@ def test_config4_tric_200_ticks_sqp_shift_through_one_call():
     x = ro.x.cpu().numpy()
     assert np.abs(x[6]).max() <= 30.0 * deg + 1e-9
     print(f"config 4: tric {B} robots x {T} ticks, SQP + shift in one call: max |v_ref| {np.abs(cmd[:, 0]).max():.3f}, "
-          f"max |alpha_ref| {np.abs(cmd[:, 1]).max() / deg:.1f} deg, max steering rate {dalpha / deg:.1f} deg/s")
+          f"max |alpha_ref| {np.abs(cmd[:, 1]).max() / deg:.1f} deg, max steering rate {dalpha / deg:.1f} deg/s; "
+          f"{wall:.2f} s for the call = {wall / T * 1e3:.2f} ms per tick")
     ctl.close()
