@@ -71,7 +71,9 @@ struct Solo {
     static constexpr int NV = S::NV, NX = S::NX, NU = S::NU, NZ = S::NZ, NC = S::NC, NB2 = S::NB2, NLU = S::NLU, NY = S::NY;
     static constexpr int N = NSTAGE;
     static constexpr int NTRI = NZ * (NZ + 1) / 2, NXTRI = NX * (NX + 1) / 2;
-    static constexpr int THREADS = ((N + 1 + 31) / 32) * 32;      // one thread per stage, whole warps
+    // one thread per stage in the stage-parallel phases; the models with four channels have 176 entries of P [B A] per stage:
+    // one per thread of six warps instead of two per thread of three (Riccati sub-phases 964 -> ~600 cycles)
+    static constexpr int THREADS = NV > 2 ? 192 : ((N + 1 + 31) / 32) * 32;
 
     // ---- shared-memory block of one stage (doubles) --------------------------------------------------------------------
     // Models with more than two channels (omni4: 81 stages x 559 doubles = 362 KB) do not fit the shared memory of an SM: their
@@ -118,7 +120,8 @@ struct Solo {
     static constexpr int O_WV = O_MM + NZ * NZ;        // NX     P rb + p of the successor stage
     static constexpr int O_GP = O_WV + NX;             // NZ     stage gradient incl. the cost-to-go of the successor
     static constexpr int O_LH = O_GP + NZ;             // NV     Luu^-1 (gradient of the controls)
-    static constexpr int O_CTL = O_LH + NV;            // LaneCtl
+    static constexpr int O_JB = (O_LH + NV + 1) & ~1;  // 2*JSZ  BIG models: double buffer of the stage's [B A] in the Riccati recursion
+    static constexpr int O_CTL = O_JB + (NV > 2 ? 2 * (((3 + 2 * NV) * (3 + 3 * NV) + 1) & ~1) : 0);            // LaneCtl
     static constexpr int CTL_D = (int)((sizeof(LaneCtl) + 7) / 8);
     static constexpr int O_SC = O_CTL + CTL_D;         // a_step
     static constexpr int O_REC = (O_SC + 3 + SOLO_NPROF + 2 + 1) & ~1;
@@ -328,13 +331,16 @@ struct Solo {
     //      multiply-adds (even and odd terms accumulate separately), the matrix row is fetched ahead of it.  The host emulation
     //      passes the vector through the stage blocks instead; the sums are formed in the same order. ---------------------------------
 #if !SOLO_HOST
-    // s0 + row . v, v spread over the lanes (component i on lane i); STRIDE: distance of the row's entries
+    // s0 + row . v, v spread over the lanes (component i on lane i); the row is fetched TWO stages ahead of its use (the
+    // recursions below keep two row buffers in registers): shared memory for the small models, L2 for the BIG ones
     template <int STRIDE>
-    __device__ __forceinline__ static double dot_shfl(const double* row, double v, double s0)
+    __device__ __forceinline__ static void load_row(double (&r)[NX], const double* row)
     {
-        double r[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) r[i] = row[i * STRIDE];
+    }
+    __device__ __forceinline__ static double dot_shfl(const double (&r)[NX], double v, double s0)
+    {
         double s1 = 0.0;
 #pragma unroll
         for (int i = 0; i < NX; i++) {
@@ -361,11 +367,18 @@ struct Solo {
         if (threadIdx.x >= 32) return;
         const int j = threadIdx.x < NX ? threadIdx.x : 0;
         double v = rec(sm, N)[R_V + j];
-#pragma unroll 2
-        for (int k = N - 1; k >= 1; k--) {
-            double* rc = rec(sm, k);
-            v = dot_shfl<NZ>(Jp(sm, k) + NU + j, v, rc[R_V + j]);
-            if (threadIdx.x < NX) rc[R_V + j] = v;
+        double ra[NX], rb[NX];
+        load_row<NZ>(ra, Jp(sm, N - 1) + NU + j);
+        load_row<NZ>(rb, Jp(sm, N - 2 >= 1 ? N - 2 : 1) + NU + j);
+        for (int k = N - 1; k >= 1; k -= 2) {
+            v = dot_shfl(ra, v, rec(sm, k)[R_V + j]);
+            if (threadIdx.x < NX) rec(sm, k)[R_V + j] = v;
+            if (k - 2 >= 1) load_row<NZ>(ra, Jp(sm, k - 2) + NU + j);
+            if (k - 1 >= 1) {
+                v = dot_shfl(rb, v, rec(sm, k - 1)[R_V + j]);
+                if (threadIdx.x < NX) rec(sm, k - 1)[R_V + j] = v;
+                if (k - 3 >= 1) load_row<NZ>(rb, Jp(sm, k - 3) + NU + j);
+            }
         }
 #endif
     }
@@ -380,11 +393,18 @@ struct Solo {
         if (threadIdx.x >= 32) return;
         const int j = threadIdx.x < NX ? threadIdx.x : 0;
         double v = rec(sm, N)[R_V + j];
-#pragma unroll 2
-        for (int k = N - 1; k >= 1; k--) {
-            double* rc = rec(sm, k);
-            v = dot_shfl<1>(pht(sm, k) + j * NXP, v, rc[R_V + j]);
-            if (threadIdx.x < NX) rc[R_V + j] = v;
+        double ra[NX], rb[NX];
+        load_row<1>(ra, pht(sm, N - 1) + j * NXP);
+        load_row<1>(rb, pht(sm, N - 2 >= 1 ? N - 2 : 1) + j * NXP);
+        for (int k = N - 1; k >= 1; k -= 2) {
+            v = dot_shfl(ra, v, rec(sm, k)[R_V + j]);
+            if (threadIdx.x < NX) rec(sm, k)[R_V + j] = v;
+            if (k - 2 >= 1) load_row<1>(ra, pht(sm, k - 2) + j * NXP);
+            if (k - 1 >= 1) {
+                v = dot_shfl(rb, v, rec(sm, k - 1)[R_V + j]);
+                if (threadIdx.x < NX) rec(sm, k - 1)[R_V + j] = v;
+                if (k - 3 >= 1) load_row<1>(rb, pht(sm, k - 3) + j * NXP);
+            }
         }
 #endif
     }
@@ -401,11 +421,18 @@ struct Solo {
         const int i = threadIdx.x < NX ? threadIdx.x : 0;
         double x = rec(sm, 0)[R_C + i];
         if (threadIdx.x < NX) { rec(sm, 0)[R_X + i] = 0.0; rec(sm, 1)[R_X + i] = x; }
-#pragma unroll 2
-        for (int k = 1; k < N; k++) {
-            double* rc = rec(sm, k);
-            x = dot_shfl<1>(phi(sm, k) + i * NXP, x, rc[R_C + i]);
-            if (threadIdx.x < NX) rc[RS + R_X + i] = x;
+        double ra[NX], rb[NX];
+        load_row<1>(ra, phi(sm, 1) + i * NXP);
+        load_row<1>(rb, phi(sm, 2 < N ? 2 : 1) + i * NXP);
+        for (int k = 1; k < N; k += 2) {
+            x = dot_shfl(ra, x, rec(sm, k)[R_C + i]);
+            if (threadIdx.x < NX) rec(sm, k + 1)[R_X + i] = x;
+            if (k + 2 < N) load_row<1>(ra, phi(sm, k + 2) + i * NXP);
+            if (k + 1 < N) {
+                x = dot_shfl(rb, x, rec(sm, k + 1)[R_C + i]);
+                if (threadIdx.x < NX) rec(sm, k + 2)[R_X + i] = x;
+                if (k + 3 < N) load_row<1>(rb, phi(sm, k + 3) + i * NXP);
+            }
         }
 #endif
     }
@@ -668,10 +695,23 @@ struct Solo {
             i4[q] = -1; j4[q] = -1;
             if (e < NXTRI) tri_decode(e, i4[q], j4[q]); else if (e < NXTRI + NX) i4[q] = e - NXTRI;
         }
+        // BIG models: [B A] of the stage is staged from the global scratch into a double buffer in shared memory, one stage ahead
+        // (16-byte asynchronous copies by the first threads of the block)
+        double* Jb = sm + O_JB;
+        auto stage_J = [&](int kk, int buf) {
+            if (BIG) {
+                for (int e = 2 * t; e < JSZ; e += 2 * nt) grp_cp16(Jb + buf * JSZ + e, Jp(sm, kk) + e);
+                grp_cp_commit();
+            }
+        };
+        stage_J(N - 1, 0);
+        grp_cp_wait<0>();
         SOLO_SYNC();
         for (int k = N - 1; k >= 0; k--) {
             double* st = sm + (size_t)k * PS;
-            const double* J = Jp(sm, k);
+            const int cur = (N - 1 - k) & 1;
+            const double* J = BIG ? Jb + cur * JSZ : Jp(sm, k);
+            if (k >= 1) stage_J(k - 1, cur ^ 1);
             const bool hasX = k > 0;
             // G = P [B A];  w = P rb + p_{k+1}
             for (int e = t; e < NX * NZ + NX; e += nt) {
@@ -785,6 +825,7 @@ struct Solo {
                     }
                 }
             }
+            grp_cp_wait<0>();
             SOLO_SYNC();
             SOLO_T(19);
         }
@@ -836,31 +877,35 @@ struct Solo {
                 for (int a = 0; a < NV; a++) st[O_UF + a] = uf[a];
             }
 #pragma unroll
-            for (int j = 0; j < NX; j++) {
-                double kf[NV];
-#pragma unroll
-                for (int a = NV - 1; a >= 0; a--) {
-                    double s = st[O_KF + a * NX + j];
-#pragma unroll
-                    for (int b = a + 1; b < NV; b++) s -= Luu[b * (b + 1) / 2 + a] * kf[b];
-                    kf[a] = s * Luu[a * (a + 1) / 2 + a];
-                }
-#pragma unroll
-                for (int a = 0; a < NV; a++) st[O_KF + a * NX + j] = kf[a];
-#pragma unroll
-                for (int i = 0; i < NX; i++) {
-                    double s = J[i * NZ + NU + j];
-#pragma unroll
-                    for (int a = 0; a < NV; a++) s -= J[i * NZ + a] * kf[a];
-                    phi(sm, k)[i * NXP + j] = s; pht(sm, k)[j * NXP + i] = s;
-                }
-            }
-#pragma unroll
             for (int i = 0; i < NX; i++) {
                 double s = st[O_RB + i];
 #pragma unroll
                 for (int a = 0; a < NV; a++) s += J[i * NZ + a] * st[O_UF + a];
                 rec(sm, k)[R_C + i] = s;
+            }
+        }
+        if (FAST) SOLO_SYNC();
+        // column j of the gain and of the closed-loop matrix of stage k: one work item per (stage, column), all threads
+        for (int e = SOLO_TID; e < N * NX; e += SOLO_NT) {
+            const int k = e / NX, j = e - k * NX;
+            double* st = sm + (size_t)k * PS;
+            const double* J = Jp(sm, k); const double* Luu = st + O_LUU;
+            double kf[NV];
+#pragma unroll
+            for (int a = NV - 1; a >= 0; a--) {
+                double s = st[O_KF + a * NX + j];
+#pragma unroll
+                for (int b = a + 1; b < NV; b++) s -= Luu[b * (b + 1) / 2 + a] * kf[b];
+                kf[a] = s * Luu[a * (a + 1) / 2 + a];
+            }
+#pragma unroll
+            for (int a = 0; a < NV; a++) st[O_KF + a * NX + j] = kf[a];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                double s = J[i * NZ + NU + j];
+#pragma unroll
+                for (int a = 0; a < NV; a++) s -= J[i * NZ + a] * kf[a];
+                phi(sm, k)[i * NXP + j] = s; pht(sm, k)[j * NXP + i] = s;
             }
         }
         SOLO_SYNC();

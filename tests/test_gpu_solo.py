@@ -1,4 +1,5 @@
-"""GPU parity of the block-per-instance K3 mapping (csrc/rti_solo.cuh, the latency path for small batches of diff / tric):
+"""GPU parity of the block-per-instance K3 mapping (csrc/rti_solo.cuh, the latency path for small batches; omni4 keeps its two
+largest per-stage arrays in a global scratch):
 against the CPU oracle on the same seeded inputs, and against the lane-cooperative kernel it replaces at those sizes."""
 import os
 
@@ -33,7 +34,8 @@ def _to_soa(a):
     return t.permute(*perm).contiguous().cuda()
 
 
-@pytest.mark.parametrize("name,B,start", [("diff", 1, 0), ("diff", 37, 100), ("diff", 300, 2000), ("tric", 1, 3), ("tric", 150, 500)])
+@pytest.mark.parametrize("name,B,start", [("diff", 1, 0), ("diff", 37, 100), ("diff", 300, 2000), ("tric", 1, 3), ("tric", 150, 500),
+                                          ("omni4", 1, 11), ("omni4", 70, 640)])
 def test_solo_matches_oracle_cold_and_warm(oracle_mod, name, B, start):
     """cold step and a second (warm) step from the persisted iterate, device-resident inputs, solo kernel forced"""
     spec, x0, yref, _ = instances(name, start, B)
@@ -63,7 +65,7 @@ def test_solo_matches_oracle_cold_and_warm(oracle_mod, name, B, start):
     s.close()
 
 
-@pytest.mark.parametrize("name", ["diff", "tric"])
+@pytest.mark.parametrize("name", ["diff", "tric", "omni4"])
 def test_solo_equals_cooperative_kernel(name):
     """the two mappings a small batch can take: equal iteration counts, results to rounding; the solo kernel is repeatable bit for bit"""
     B = 96
