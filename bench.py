@@ -180,7 +180,7 @@ def cpu_latency(model: str, calls: int) -> dict:
         o.rti_batch(x0, yref, x, u, nthreads=1)
         ts.append((time.perf_counter() - t0) * 1e6)
     ts = np.array(ts[20:])
-    return {"what": "one cold-iterate diff RTI solve, oracle port, 1 thread", "calls": calls,
+    return {"what": f"one cold-iterate {model} RTI solve, oracle port, 1 thread", "calls": calls,
             "p50_us": float(np.percentile(ts, 50)), "p95_us": float(np.percentile(ts, 95)), "p99_us": float(np.percentile(ts, 99))}
 
 
@@ -205,7 +205,7 @@ def gpu_latency(model: str, device: int, calls: int = 1000, warm: int = 100) -> 
         out = s.solve_host(x0, yref, out=out)
         ts.append((time.perf_counter() - t0) * 1e6)
     ts = np.array(ts)
-    r = {"what": "batch = 1 cold-iterate diff RTI solve through nmpc_rti_solve_host (C ABI, host buffers)", "calls": calls,
+    r = {"what": f"batch = 1 cold-iterate {model} RTI solve through nmpc_rti_solve_host (C ABI, host buffers)", "calls": calls,
          "warmup": warm, "p50_us": float(np.percentile(ts, 50)), "p95_us": float(np.percentile(ts, 95)),
          "p99_us": float(np.percentile(ts, 99)), "qp_iter": int(out["qp_iter"][0])}
     s.close()
@@ -375,6 +375,14 @@ def run_ours(args):
         latency = gpu_latency(MODEL, local)
         if not args.no_cpu:
             latency["cpu_port"] = cpu_latency(MODEL, 200)
+        # the other two models of the package, the same measurement (300 calls each)
+        latency["other_models"] = {}
+        for m in ("tric", "omni4"):
+            g = gpu_latency(m, local, calls=300, warm=30)
+            rec = {"p50_us": g["p50_us"], "p99_us": g["p99_us"], "qp_iter": g["qp_iter"]}
+            if not args.no_cpu:
+                rec["cpu_port_p50_us"] = cpu_latency(m, 60)["p50_us"]
+            latency["other_models"][m] = rec
 
     # measured DRAM traffic of K3 per solve (ncu dram__bytes over all K3 launches of one step, see
     # tools/ncu_launches.py --json and profiles/): what the streaming roofline is computed from
