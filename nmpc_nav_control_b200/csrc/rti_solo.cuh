@@ -120,8 +120,7 @@ struct Solo {
     static constexpr int O_WV = O_MM + NZ * NZ;        // NX     P rb + p of the successor stage
     static constexpr int O_GP = O_WV + NX;             // NZ     stage gradient incl. the cost-to-go of the successor
     static constexpr int O_LH = O_GP + NZ;             // NV     Luu^-1 (gradient of the controls)
-    static constexpr int O_PIV = O_LH + NV;            // NV*NV  pivot columns of the control block's factorisation
-    static constexpr int O_JB = (O_PIV + NV * NV + 1) & ~1;  // 2*JSZ  BIG models: double buffer of the stage's [B A] in the Riccati recursion
+    static constexpr int O_JB = (O_LH + NV + 1) & ~1;  // 2*JSZ  BIG models: double buffer of the stage's [B A] in the Riccati recursion
     static constexpr int O_CTL = O_JB + (NV > 2 ? 2 * (((3 + 2 * NV) * (3 + 3 * NV) + 1) & ~1) : 0);            // LaneCtl
     static constexpr int CTL_D = (int)((sizeof(LaneCtl) + 7) / 8);
     static constexpr int O_SC = O_CTL + CTL_D;         // a_step
@@ -751,74 +750,58 @@ struct Solo {
             }
             SOLO_SYNC();
             SOLO_T(17);
-            // Cholesky of the control block as a right-looking elimination on the augmented matrix [Muu | S' | g_u] (NV rows,
-            // NV + NX + 1 columns): ONE COLUMN PER THREAD of the first warp, the column in registers; before pivot a the owner
-            // of column a publishes its entries a..NV-1, every thread forms the pivot's reciprocal square root and the
-            // multipliers itself and updates its own column.  What is left in the columns is Luu^-1 S = K and Luu^-1 g_u; the
-            // chain is NV x (store, warp barrier, load, rsqrt, two multiply-adds) instead of every thread walking the whole factor.
-            {
-                constexpr int NCOL = NV + NX + 1;
-                static_assert(NCOL <= 32, "one warp");
-                double colr[SOLO_HOST ? NCOL : 1][NV], Lr[SOLO_HOST ? NCOL : 1][NLU];
-                double* PIV = sm + O_PIV;
-                for (int c = t; c < NCOL; c += nt) {
-                    double (&col)[NV] = colr[SOLO_HOST ? c : 0];
-#pragma unroll
-                    for (int r = 0; r < NV; r++)
-                        col[r] = c < NV ? (r >= c ? Mm[r * NZ + c] : Mm[c * NZ + r])
-                               : c < NV + NX ? (hasX ? Mm[(NU + c - NV) * NZ + r] : 0.0) : GP[r];
-                }
+            // Cholesky of the control block; item j < NX: column j of K = Luu^-1 S; item NX: Luu^-1 g_u, the feed-forward control
+            for (int j = t; j <= NX; j += nt) {
+                double Luu[NLU];
 #pragma unroll
                 for (int a = 0; a < NV; a++) {
-                    for (int c = t; c < NCOL; c += nt) {
-                        if (c == a) {
-                            const double (&col)[NV] = colr[SOLO_HOST ? c : 0];
+                    double d = Mm[a * NZ + a];
 #pragma unroll
-                            for (int r = a; r < NV; r++) PIV[a * NV + r] = col[r];
-                        }
-                    }
-                    if (t < 32) SOLO_WSYNC();
-                    for (int c = t; c < NCOL; c += nt) {
-                        double (&col)[NV] = colr[SOLO_HOST ? c : 0];
-                        double (&L)[NLU] = Lr[SOLO_HOST ? c : 0];
-                        const double d = PIV[a * NV + a];
+                    for (int c = 0; c < a; c++) d -= Luu[a * (a + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
 #if SOLO_HOST
-                        const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                    const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
 #else
-                        const double inv = d > 0.0 ? rsqrt(d) : 0.0;
+                    const double inv = d > 0.0 ? rsqrt(d) : 0.0;
 #endif
-                        L[a * (a + 1) / 2 + a] = inv;
-                        const double xa = col[a] * inv;
-                        col[a] = xa;
+                    Luu[a * (a + 1) / 2 + a] = inv;
 #pragma unroll
-                        for (int r = a + 1; r < NV; r++) {
-                            const double l = PIV[a * NV + r] * inv;
-                            L[r * (r + 1) / 2 + a] = l;
-                            col[r] -= l * xa;
-                        }
+                    for (int b = a + 1; b < NV; b++) {
+                        double s = Mm[b * NZ + a];
+#pragma unroll
+                        for (int c = 0; c < a; c++) s -= Luu[b * (b + 1) / 2 + c] * Luu[a * (a + 1) / 2 + c];
+                        Luu[b * (b + 1) / 2 + a] = s * inv;
                     }
                 }
-                for (int c = t; c < NCOL; c += nt) {
-                    const double (&col)[NV] = colr[SOLO_HOST ? c : 0];
-                    const double (&L)[NLU] = Lr[SOLO_HOST ? c : 0];
-                    if (c >= NV && c < NV + NX) {
+                if (j < NX) {
+                    double kh[NV];
 #pragma unroll
-                        for (int r = 0; r < NV; r++) st[O_KF + r * NX + (c - NV)] = col[r];
-                    } else if (c == NV + NX) {
-                        double uf[NV];
+                    for (int a = 0; a < NV; a++) {
+                        double s = hasX ? Mm[(NU + j) * NZ + a] : 0.0;
 #pragma unroll
-                        for (int r = 0; r < NV; r++) LH[r] = col[r];
-#pragma unroll
-                        for (int r = NV - 1; r >= 0; r--) {
-                            double sacc = -col[r];
-#pragma unroll
-                            for (int q = r + 1; q < NV; q++) sacc -= L[q * (q + 1) / 2 + r] * uf[q];
-                            uf[r] = sacc * L[r * (r + 1) / 2 + r];
-                            st[O_UF + r] = uf[r];
-                        }
-#pragma unroll
-                        for (int q = 0; q < NLU; q++) st[O_LUU + q] = L[q];
+                        for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * kh[c];
+                        kh[a] = s * Luu[a * (a + 1) / 2 + a];
+                        st[O_KF + a * NX + j] = kh[a];
                     }
+                } else {
+                    double lh[NV], uf[NV];
+#pragma unroll
+                    for (int a = 0; a < NV; a++) {
+                        double s = GP[a];
+#pragma unroll
+                        for (int c = 0; c < a; c++) s -= Luu[a * (a + 1) / 2 + c] * lh[c];
+                        lh[a] = s * Luu[a * (a + 1) / 2 + a];
+                        LH[a] = lh[a];
+                    }
+#pragma unroll
+                    for (int a = NV - 1; a >= 0; a--) {
+                        double s = -lh[a];
+#pragma unroll
+                        for (int b = a + 1; b < NV; b++) s -= Luu[b * (b + 1) / 2 + a] * uf[b];
+                        uf[a] = s * Luu[a * (a + 1) / 2 + a];
+                        st[O_UF + a] = uf[a];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NLU; q++) st[O_LUU + q] = Luu[q];
                 }
             }
             SOLO_SYNC();
