@@ -778,6 +778,8 @@ struct nmpc_solver {
     int *d_qp_status = nullptr;
     // host-call staging
     double *d_stage_in = nullptr, *d_x0bar = nullptr, *d_yref = nullptr, *d_We = nullptr, *d_out = nullptr, *d_out_aos = nullptr;
+    // small-batch host path (nmpc_rti_solve_host with B <= SMALL_HOST_B): one pinned staging buffer each way, one copy each way
+    double *h_small = nullptr, *d_small = nullptr;
     int *d_status = nullptr, *d_iter = nullptr;
     double *d_stats = nullptr;                   // [8][cap] statistics of the last host call
     int last_host_B = 0;
@@ -920,6 +922,8 @@ extern "C" int nmpc_destroy(nmpc_solver* s)
     cudaFree(s->d_vref); cudaFree(s->d_cin); cudaFree(s->d_cnref); cudaFree(s->d_tab); cudaFree(s->d_x); cudaFree(s->d_u); cudaFree(s->d_ws); cudaFree(s->d_qp_status);
     cudaFree(s->d_ctl_d); cudaFree(s->d_ctl_i); cudaFree(s->d_cnt);
     cudaFree(s->d_solo_scr); cudaFree(s->d_ws_g); cudaFree(s->d_list); cudaFree(s->d_map); cudaFree(s->d_ctl_g);
+    if (s->h_small) cudaFreeHost(s->h_small);
+    cudaFree(s->d_small);
     cudaFree(s->d_stage_in); cudaFree(s->d_x0bar); cudaFree(s->d_yref); cudaFree(s->d_We); cudaFree(s->d_out); cudaFree(s->d_out_aos);
     cudaFree(s->d_status); cudaFree(s->d_iter); cudaFree(s->d_stats);
     cudaFree(s->d_sqp_active); cudaFree(s->d_sqp_iter); cudaFree(s->d_sqp_qp); cudaFree(s->d_sqp_stepn);
@@ -1494,6 +1498,75 @@ extern "C" int nmpc_get_iterate_host(nmpc_solver* s, int B, double* x, double* u
     return 0;
 }
 
+// ---- small-batch host path: the ROS drop-in (one robot per call) and small fleets.  What the general path below does with one
+// copy and one transposition kernel per argument (nine launches and six copies around the solve, the device-to-host ones from
+// pageable memory and therefore each a round trip of its own) is done here with ONE pinned staging buffer each way: inputs
+// packed [x0bar | yref | We] on the host, one H2D, one kernel that scatters them into the structure-of-arrays buffers, the solve,
+// one kernel that gathers [u_0 | x_1 | status | qp_iter], one D2H.
+constexpr int SMALL_HOST_B = 64;
+__global__ void k_small_in(int B, int nx, int R, int hasWe, const double* __restrict__ in, double* __restrict__ x0bar,
+                           double* __restrict__ yref, double* __restrict__ We)
+{
+    const int per = nx + R + (hasWe ? nx : 0);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * per; e += gridDim.x * blockDim.x) {
+        const int i = e / per, r = e - i * per;                       // output index: instance fastest within a row
+        // rows 0..nx-1: x0bar, nx..nx+R-1: yref, then We; the packed input holds the three arrays back to back, each instance-major
+        if (r < nx) x0bar[(size_t)r * B + i] = in[(size_t)i * nx + r];
+        else if (r < nx + R) yref[(size_t)(r - nx) * B + i] = in[(size_t)B * nx + (size_t)i * R + (r - nx)];
+        else We[(size_t)(r - nx - R) * B + i] = in[(size_t)B * (nx + R) + (size_t)i * nx + (r - nx - R)];
+    }
+}
+__global__ void k_small_out(int B, int nx, int nu, int ld, const double* __restrict__ x, const double* __restrict__ u,
+                            const int* __restrict__ status, const int* __restrict__ iter, double* __restrict__ out)
+{
+    const int per = nu + nx;
+    int* io = reinterpret_cast<int*>(out + (size_t)B * per);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * (per + 1); e += gridDim.x * blockDim.x) {
+        if (e < B * per) {
+            const int i = e / per, r = e - i * per;
+            if (r < nu) out[(size_t)i * nu + r] = u[(size_t)r * ld + i];                               // u_0
+            else out[(size_t)B * nu + (size_t)i * nx + (r - nu)] = x[(size_t)(nx + r - nu) * ld + i];  // x_1
+        } else {
+            const int i = e - B * per;
+            io[i] = status[i]; io[B + i] = iter[i];
+        }
+    }
+}
+static int solve_host_small(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
+                            double* u0, double* x1, int* status, int* qp_iter)
+{
+    const int nx = s->mi.nx, nu = s->mi.nu, ny = nx + nu;
+    const int R = (NSTAGE + 1) * nyref;
+    if (!s->h_small) {
+        const size_t cap_in = (size_t)SMALL_HOST_B * (2 * nx + (size_t)(NSTAGE + 1) * ny);
+        CK(cudaMallocHost(&s->h_small, cap_in * sizeof(double)));
+        CK(cudaMalloc(&s->d_small, cap_in * sizeof(double)));
+    }
+    cudaStream_t st = s->own_stream;
+    const size_t n_in = (size_t)B * (nx + R + (We ? nx : 0));
+    memcpy(s->h_small, x0bar, (size_t)B * nx * sizeof(double));
+    memcpy(s->h_small + (size_t)B * nx, yref, (size_t)B * R * sizeof(double));
+    if (We) memcpy(s->h_small + (size_t)B * (nx + R), We, (size_t)B * nx * sizeof(double));
+    CK(cudaMemcpyAsync(s->d_small, s->h_small, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_small_in<<<(int)((n_in + 255) / 256), 256, 0, st>>>(B, nx, R, We ? 1 : 0, s->d_small, s->d_x0bar, s->d_yref, s->d_We);
+    int rc = nmpc_rti_solve_device(s, B, s->d_x0bar, s->d_yref, nyref, We ? s->d_We : nullptr, nullptr, nullptr, 0,
+                                   s->d_status, s->d_iter, s->d_stats, st);
+    if (rc) return rc;
+    s->last_host_B = B;
+    const size_t n_out = (size_t)B * (nu + nx);                       // doubles, followed by 2 B ints
+    k_small_out<<<(int)((n_out + B + 255) / 256), 256, 0, st>>>(B, nx, nu, s->cap, s->d_x, s->d_u, s->d_status, s->d_iter, s->d_small);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->h_small, s->d_small, n_out * sizeof(double) + 2 * (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    s->last_launches += 2;
+    CK(cudaStreamSynchronize(st));
+    memcpy(u0, s->h_small, (size_t)B * nu * sizeof(double));
+    memcpy(x1, s->h_small + (size_t)B * nu, (size_t)B * nx * sizeof(double));
+    const int* io = reinterpret_cast<const int*>(s->h_small + n_out);
+    memcpy(status, io, (size_t)B * sizeof(int));
+    memcpy(qp_iter, io + B, (size_t)B * sizeof(int));
+    return 0;
+}
+
 extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
                                    double* u0, double* x1, int* status, int* qp_iter)
 {
@@ -1504,6 +1577,7 @@ extern "C" int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, c
     if (nyref != 3 && nyref != ny) return set_err(NMPC_E_ARG, "nyref must be 3 or ny");
     CK(cudaSetDevice(s->device));
     int rc = ensure_staging(s); if (rc) return rc;
+    if (B <= SMALL_HOST_B) return solve_host_small(s, B, x0bar, yref, nyref, We, u0, x1, status, qp_iter);
     cudaStream_t st = s->own_stream;
     // H2D: x0bar and yref land instance-major and are transposed on the device
     {

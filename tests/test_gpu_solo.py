@@ -109,3 +109,36 @@ def test_solo_per_instance_terminal_weight_and_nan_isolation(oracle_mod):
     keep = np.arange(B) != 5
     assert np.array_equal(x2[keep], x[keep]) and np.array_equal(u2[keep], u[keep])
     s.close()
+
+
+@pytest.mark.parametrize("name,nyfull", [("diff", False), ("diff", True), ("tric", False), ("omni4", True)])
+def test_small_batch_host_path_equals_the_general_host_path(oracle_mod, name, nyfull):
+    """nmpc_rti_solve_host stages batches of at most 64 instances through one pinned buffer each way (the ROS drop-in's call,
+    NMPCNavControlDiff.cpp:96-169: x0 / yref / W_e in, u_0 / x_1 / status out).  The instances of a 65-instance call (general
+    path: one copy and one transposition per argument) solved in calls of 1, 7 and 57 give the same bits, with and without the
+    per-instance W_e, with pose-only and full reference rows; and the oracle agrees."""
+    B = 65
+    spec, x0, yref, _ = instances(name, 4242, B, pose_only=not nyfull)
+    tb = spec.codegen_defaults()
+    We = np.tile(np.asarray(tb["We"], dtype=np.float64), (B, 1))
+    We[::3, :3] *= 100.0
+    for use_we in (False, True):
+        w = We if use_we else None
+        s = _solver(name, B, solo_max=100000)
+        s.reset()
+        big = {k: v.copy() for k, v in s.solve_host(x0, yref, We=w).items()}
+        s.close()
+        yfull = np.zeros((B, spec.n + 1, spec.ny)); yfull[:, :, :yref.shape[2]] = yref     # reference rows beyond the pose are zero
+        ref = oracle_solve(oracle_mod, name, x0, yfull, We=w)
+        assert (big["qp_iter"] == ref["qp_iter"]).all() and (big["status"] == 0).all()
+        assert parity_report(big["u0"], ref["u"][:, 0], ref["lin_res"])[0] == 0
+        lo = 0
+        for n in (1, 7, 57):
+            s = _solver(name, n, solo_max=100000)
+            s.reset()
+            sl = slice(lo, lo + n)
+            out = s.solve_host(x0[sl], yref[sl], We=None if w is None else w[sl])
+            for k in ("u0", "x1", "status", "qp_iter"):
+                assert np.array_equal(out[k], big[k][sl]), (name, use_we, n, k)
+            s.close()
+            lo += n
