@@ -40,6 +40,9 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #ifndef NMPC_SW_TILES
 #define NMPC_SW_TILES 1                 // tiles (warps) per CTA of a sweep kernel (1: the omni4 factorising sweep fits more warps per SM)
 #endif
+#ifndef NMPC_B_STAGE_IMAGE
+#define NMPC_B_STAGE_IMAGE 1            // factorising sweep of diff / tric: iterate and step rows of the next stage copied asynchronously into shared memory
+#endif
 #define NMPC_SCRATCH_STRIDE (32 * NMPC_SW_TILES)
 #else
 #define NMPC_SCRATCH_STRIDE 1

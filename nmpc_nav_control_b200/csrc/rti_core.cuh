@@ -156,6 +156,15 @@ struct LinLean {
     NMPC_HD double r_u(int c) const { return lti[3 * NV + c]; }
 };
 
+#if defined(__CUDA_ARCH__)
+// 8-byte asynchronous global -> shared copy (lane-private image of the factorising sweep)
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+}
+#endif
+
 template <class M>
 struct Rti {
     static constexpr int NV = M::NV, NP = M::NP, NX = 3 + 2 * NV, NU = NV, NZ = NX + NU, NY = NZ;
@@ -531,6 +540,7 @@ struct Rti {
     // front, one memory round trip per stage, ~400 bytes of spills that stay in L1.  Streamed (below; omni4): channel by
     // channel, few values live, several dependent round trips per stage.  Measured, 65,536 instances, K3 per step: diff
     // 34.5 ms whole / 37.7 ms streamed, tric 23.6 / 27.1, omni4 139 / 119 (whole-stage omni4 spills 1.9 KB in this half alone).
+    template <bool IMAGE = false>
     NMPC_HD static void stage_B_update_whole(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
                                        const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
                                        double* gu, double* gx, double* rb, double* Gam)
@@ -548,11 +558,51 @@ struct Rti {
         double ll[NB2], lu[NB2], tl[NB2], tu[NB2], dl[NB2], du_[NB2];
 #pragma unroll
         for (int b = 0; b < NB2; b++) { dl[b] = in.lin[(R::DLB + b) * LANES]; du_[b] = in.lin[(R::DUB + b) * LANES]; }
-
+        // Every global load of the stage is issued HERE, unconditionally, before anything is computed (the fence below keeps
+        // ptxas from sinking them to their uses): one memory round trip per stage.  With the loads left inside the `act` /
+        // hasU / hasX branches the compiler cannot move them above the branches, and the stage waits on eight dependent
+        // round trips (ncu: 59 % of the sweep's stall samples on the long scoreboard, 19 % on the four divisions by t alone).
+        // Rows that a stage does not have (controls of stage N, states of stage 0) exist in the tile; what is read there is
+        // discarded by the selects below.
+        const int kt = hasU ? k : 0;                                   // the tables have N rows
         L lin;
+        load_lin(in.lin, tb.lti + kt * 4 * NV, tb.thr + kt * NC, lin);
+        double b0[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) b0[i] = in.lin[(R::B0 + i) * LANES];
+        double dzu[NV], dzx[NX], mcl[NB2], mcu[NB2];
+        if (!first) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) zu[c] = in.it[(R::Z + c) * LANES];
+#pragma unroll
+            for (int j = 0; j < NX; j++) { zx[j] = in.it[(R::Z + NU + j) * LANES]; pin[j] = in.it[(R::PI + j) * LANES]; }
+#pragma unroll
+            for (int b = 0; b < NB2; b++) {
+                ll[b] = in.it[(R::LAM + b) * LANES]; lu[b] = in.it[(R::LAM + NB2 + b) * LANES];
+                tl[b] = in.it[(R::T + b) * LANES];   tu[b] = in.it[(R::T + NB2 + b) * LANES];
+            }
+#if defined(__CUDA_ARCH__)
+            if (IMAGE) {
+                // in.st points at the lane's shared-memory image of the step rows, copied while the previous stage was
+                // factorised: the loads above are in flight, the reads below wait for nothing
+                NMPC_PHASE_FENCE();
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            }
+#endif
+#pragma unroll
+            for (int c = 0; c < NV; c++) dzu[c] = in.st[(R::DZ + c) * LANES];
+#pragma unroll
+            for (int j = 0; j < NX; j++) dzx[j] = in.st[(R::DZ + NU + j) * LANES];
+#pragma unroll
+            for (int b = 0; b < NB2; b++) { mcl[b] = in.st[(R::MC + b) * LANES]; mcu[b] = in.st[(R::MC + NB2 + b) * LANES]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NX; j++) zx[j] = in.it[(R::Z + NU + j) * LANES];
+        }
+        if (!IMAGE) NMPC_PHASE_FENCE();
+
         double v1u[NV], v1x[NX], v2u[NV], v2x[NX];
         if (hasU) {
-            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
             double pio[NX], dpi[NX];
 #pragma unroll
             for (int j = 0; j < NX; j++) { pio[j] = sc[(C::SC_PIO + j) * PSTRIDE]; dpi[j] = sc[(C::SC_DPI + j) * PSTRIDE]; }
@@ -571,7 +621,7 @@ struct Rti {
 #pragma unroll
             for (int c = 0; c < NV; c++) zu[c] = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; j++) { zx[j] = hasX ? 0.0 : in.it[(R::Z + NU + j) * LANES]; pin[j] = 0.0; pi_old[j] = 0.0; }
+            for (int j = 0; j < NX; j++) { if (hasX) zx[j] = 0.0; pin[j] = 0.0; pi_old[j] = 0.0; }
 #pragma unroll
             for (int b = 0; b < NB2; b++) {
                 const bool act = (b < NV) ? hasU : hasX;
@@ -588,24 +638,22 @@ struct Rti {
 #pragma unroll
             for (int j = 0; j < NX; j++) sc[(C::SC_DPI + j) * PSTRIDE] = 0.0;
         } else {
-            double dzu[NV], dzx[NX];
+            if (!hasU) {
 #pragma unroll
-            for (int c = 0; c < NV; c++) { zu[c] = in.it[(R::Z + c) * LANES]; dzu[c] = hasU ? in.st[(R::DZ + c) * LANES] : 0.0; }
-#pragma unroll
-            for (int j = 0; j < NX; j++) {
-                zx[j] = in.it[(R::Z + NU + j) * LANES];
-                dzx[j] = hasX ? in.st[(R::DZ + NU + j) * LANES] : 0.0;
-                pin[j] = hasX ? in.it[(R::PI + j) * LANES] : 0.0;
-                pi_old[j] = pin[j];
+                for (int c = 0; c < NV; c++) dzu[c] = 0.0;
             }
+            if (!hasX) {
+#pragma unroll
+                for (int j = 0; j < NX; j++) { dzx[j] = 0.0; pin[j] = 0.0; }
+            }
+#pragma unroll
+            for (int j = 0; j < NX; j++) pi_old[j] = pin[j];
             double ldo[NB2], dld[NB2];   // (lam_u - lam_l) old, (dlam_l - dlam_u)
 #pragma unroll
             for (int b = 0; b < NB2; b++) {
                 const bool act = (b < NV) ? hasU : hasX;
                 if (act) {
-                    ll[b] = in.it[(R::LAM + b) * LANES]; lu[b] = in.it[(R::LAM + NB2 + b) * LANES];
-                    tl[b] = in.it[(R::T + b) * LANES];   tu[b] = in.it[(R::T + NB2 + b) * LANES];
-                    const double mc_l = in.st[(R::MC + b) * LANES], mc_u = in.st[(R::MC + NB2 + b) * LANES];
+                    const double mc_l = mcl[b], mc_u = mcu[b];
                     const double zb = (b < NV) ? zu[b] : zx[3 + b];
                     const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
                     const double rd_l = dl[b] - zb + tl[b], rd_u = -du_[b] + zb + tu[b];
@@ -661,7 +709,7 @@ struct Rti {
             apply(lin, zu, zx, rb);
 #pragma unroll
             for (int i = 0; i < NX; i++) {
-                rb[i] += in.lin[(R::B0 + i) * LANES] - sc[(C::SC_XN + i) * PSTRIDE];
+                rb[i] += b0[i] - sc[(C::SC_XN + i) * PSTRIDE];
                 cy.nb = fmax(cy.nb, fabs(rb[i]));
             }
         }
@@ -919,7 +967,7 @@ struct Rti {
                                        double* gu, double* gx, double* rb, double* Gam)
     {
         if (LEAN) stage_B_update_streamed(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
-        else stage_B_update_whole(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
+        else stage_B_update_whole<false>(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
     }
 
     // phase 2 of a B stage: one step of the Riccati recursion.
@@ -1080,6 +1128,21 @@ struct Rti {
                                 bool delta, double sigmu, double mcw, CarryF& cy)
     {
         const bool hasU = k < NSTAGE, hasX = k > 0;
+        // the constraint rows of the stage are loaded unconditionally, ahead of the arithmetic (rows that the stage does not
+        // have exist in the tile and are discarded): inside the `act` branches every component waited for its own round trip
+        double ll_[NB2], lu_[NB2], tl_[NB2], tu_[NB2], zb_[NB2], dlb_[NB2], dub_[NB2], mcl_[NB2], mcu_[NB2];
+        auto load_rows = [&](int b) {
+            ll_[b] = in.it[(R::LAM + b) * LANES]; lu_[b] = in.it[(R::LAM + NB2 + b) * LANES];
+            tl_[b] = in.it[(R::T + b) * LANES];   tu_[b] = in.it[(R::T + NB2 + b) * LANES];
+            zb_[b] = (b < NV) ? in.it[(R::Z + b) * LANES] : in.it[(R::Z + NU + 3 + b) * LANES];
+            dlb_[b] = in.lin[(R::DLB + b) * LANES]; dub_[b] = in.lin[(R::DUB + b) * LANES];
+            if (delta) { mcl_[b] = in.st[(R::MC + b) * LANES]; mcu_[b] = in.st[(R::MC + NB2 + b) * LANES]; }
+        };
+        constexpr bool HOIST = !LEAN;          // four channels: 72 values do not fit the 128 registers of the solve sweeps
+        if (HOIST) {
+#pragma unroll
+            for (int b = 0; b < NB2; b++) load_rows(b);
+        }
         double du[NV];
 #pragma unroll
         for (int c = 0; c < NV; c++) du[c] = 0.0;
@@ -1100,15 +1163,16 @@ struct Rti {
         for (int b = 0; b < NB2; b++) {
             const bool act = (b < NV) ? hasU : hasX;
             if (act) {
-                const double ll = in.it[(R::LAM + b) * LANES], lu = in.it[(R::LAM + NB2 + b) * LANES];
-                const double tl = in.it[(R::T + b) * LANES], tu = in.it[(R::T + NB2 + b) * LANES];
-                const double zb = (b < NV) ? in.it[(R::Z + b) * LANES] : in.it[(R::Z + NU + 3 + b) * LANES];
+                if (!HOIST) load_rows(b);
+                const double ll = ll_[b], lu = lu_[b];
+                const double tl = tl_[b], tu = tu_[b];
+                const double zb = zb_[b];
                 const double dzb = (b < NV) ? dzu[b] : dzx[3 + b];
-                const double rd_l = in.lin[(R::DLB + b) * LANES] - zb + tl, rd_u = -in.lin[(R::DUB + b) * LANES] + zb + tu;
+                const double rd_l = dlb_[b] - zb + tl, rd_u = -dub_[b] + zb + tu;
                 double rm_l = ll * tl - o.tau_min, rm_u = lu * tu - o.tau_min;
                 if (delta) {
-                    rm_l += mcw * in.st[(R::MC + b) * LANES] - sigmu;
-                    rm_u += mcw * in.st[(R::MC + NB2 + b) * LANES] - sigmu;
+                    rm_l += mcw * mcl_[b] - sigmu;
+                    rm_u += mcw * mcu_[b] - sigmu;
                 }
                 const double dt_l = dzb - rd_l, dt_u = -dzb - rd_u;
                 const double dl_l = -(ll * dt_l + rm_l) / tl, dl_u = -(lu * dt_u + rm_u) / tu;
@@ -1145,6 +1209,17 @@ struct Rti {
     NMPC_HD static void stage_Bd(int k, const StageIn& in, const StageOut& out, const Tables& tb, double sigmu, double mcw, CarryD& cy)
     {
         const bool hasU = k < NSTAGE, hasX = k > 0;
+        // the constraint rows are loaded unconditionally ahead of the arithmetic, as in stage_F
+        double tl_[NB2], tu_[NB2], mcl_[NB2], mcu_[NB2];
+        auto load_rows = [&](int b) {
+            tl_[b] = in.it[(R::T + b) * LANES]; tu_[b] = in.it[(R::T + NB2 + b) * LANES];
+            mcl_[b] = in.st[(R::MC + b) * LANES]; mcu_[b] = in.st[(R::MC + NB2 + b) * LANES];
+        };
+        constexpr bool HOIST = !LEAN;
+        if (HOIST) {
+#pragma unroll
+            for (int b = 0; b < NB2; b++) load_rows(b);
+        }
         double qu[NV], qx[NX];
 #pragma unroll
         for (int c = 0; c < NV; c++) qu[c] = 0.0;
@@ -1159,8 +1234,9 @@ struct Rti {
         for (int b = 0; b < NB2; b++) {
             const bool act = (b < NV) ? hasU : hasX;
             if (act) {
-                const double tl = in.it[(R::T + b) * LANES], tu = in.it[(R::T + NB2 + b) * LANES];
-                const double g = (mcw * in.st[(R::MC + b) * LANES] - sigmu) / tl - (mcw * in.st[(R::MC + NB2 + b) * LANES] - sigmu) / tu;
+                if (!HOIST) load_rows(b);
+                const double tl = tl_[b], tu = tu_[b];
+                const double g = (mcw * mcl_[b] - sigmu) / tl - (mcw * mcu_[b] - sigmu) / tu;
                 if (b < NV) qu[b] += g; else qx[3 + b] += g;
             }
         }
@@ -1363,6 +1439,32 @@ struct Rti {
             if (c.done) return;
             const double a = before_B(c);
             CarryB cy; cy.init(scratch);
+#if defined(__CUDA_ARCH__) && NMPC_B_STAGE_IMAGE
+            if (!LEAN) {
+                // The step rows of a stage (ST[DZ, MC]) travel through a lane-private image in shared memory behind the carry
+                // columns: the 8-byte asynchronous copies of stage k-1 are issued between the two halves of stage k, so they are
+                // in flight during its Riccati half and need no registers.
+                double* img = scratch + (size_t)CarryB::SC_N * PSTRIDE;
+                auto fetch = [&](int k) {
+                    const double* st = tile_lane + R::OFF_ST + (size_t)k * R::NF_ST * LANES;
+#pragma unroll
+                    for (int f = 0; f < R::DZA; f++) cp_async8(img + f * PSTRIDE, st + f * LANES);
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+                };
+                fetch(NSTAGE);
+#pragma unroll 1
+                for (int k = NSTAGE; k >= 0; k--) {
+                    StageIn in = tile_stage_in<R>(tile_lane, k);
+                    const StageOut out = tile_stage_out<R>(tile_lane, k);
+                    in.st = img;
+                    double gu[NV], gx[NX], rb[NX], Gam[NB2];
+                    stage_B_update_whole<true>(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy, gu, gx, rb, Gam);
+                    NMPC_PHASE_FENCE();
+                    if (k > 0) fetch(k - 1);
+                    stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam);
+                }
+            } else
+#endif
             sweep_lane<SW_B>(tile_lane, [&](int k, const StageIn& in, const StageOut& out) {
                 stage_B(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy); });
             after_B(c, cy, o, false);

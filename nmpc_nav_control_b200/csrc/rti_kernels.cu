@@ -1121,7 +1121,7 @@ static int solve_device_t(nmpc_solver* s, int B, const double* d_x0bar, const do
             const int ldc = s->chunk;
             const int nb = (n + LANES * SW_TILES - 1) / (LANES * SW_TILES), nt = LANES * SW_TILES;
             int* act = s->d_cnt;                 // act[it]: lanes entering iteration it
-            const size_t smB = (size_t)S::CarryB::SC_N * NMPC_SCRATCH_STRIDE * sizeof(double);
+            const size_t smB = (size_t)(S::CarryB::SC_N + ((NMPC_B_STAGE_IMAGE && !S::LEAN) ? S::R::DZA : 0)) * NMPC_SCRATCH_STRIDE * sizeof(double);
             bool& attr_set = s->sweep_attr_set;
             if (!attr_set) {
                 CK(cudaFuncSetAttribute(k_sweep<M, S::SW_B_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
