@@ -754,7 +754,29 @@ struct Rti {
     // actual c, ref c} needs from the rest of the stage is the pose part of the successor's multipliers (p0, d0) and, for
     // the dynamics residual, three running sums of the pose rows of [A B] z.  One bounded component (control or reference state):
     struct Bnd { double ldo, dld, lnew, gam, Gam, znew; };
-    NMPC_HD static void bound_component(bool act, bool first, int b, double zb, double dzb, const StageInR& in, const StageOutR& out,
+    // The rows of one bounded component / one state component, loaded unconditionally at the top of its channel (rows that a
+    // stage does not have exist in the tile and are discarded): left inside the `act` / hasX branches, every component waited
+    // for a memory round trip of its own.
+    struct BndRows { double dl, du, ll, lu, tl, tu, mcl, mcu; };
+    struct StRows { double q, z, dz, pi; };
+    NMPC_HD static void load_bound_rows(int b, bool first, const StageInR& in, BndRows& w)
+    {
+        w.dl = in.lin[(R::DLB + b) * LANES]; w.du = in.lin[(R::DUB + b) * LANES];
+        w.ll = w.lu = w.tl = w.tu = w.mcl = w.mcu = 0.0;
+        if (!first) {
+            w.ll = in.it[(R::LAM + b) * LANES]; w.lu = in.it[(R::LAM + NB2 + b) * LANES];
+            w.tl = in.it[(R::T + b) * LANES];   w.tu = in.it[(R::T + NB2 + b) * LANES];
+            w.mcl = in.st[(R::MC + b) * LANES]; w.mcu = in.st[(R::MC + NB2 + b) * LANES];
+        }
+    }
+    NMPC_HD static void load_state_rows(int j, bool first, const StageInR& in, StRows& w)
+    {
+        w.q = in.lin[(R::Q + NU + j) * LANES];
+        w.z = in.it[(R::Z + NU + j) * LANES];
+        w.dz = 0.0; w.pi = 0.0;
+        if (!first) { w.dz = in.st[(R::DZ + NU + j) * LANES]; w.pi = in.it[(R::PI + j) * LANES]; }
+    }
+    NMPC_HD static void bound_component(bool act, bool first, int b, double zb, double dzb, const BndRows& w, const StageOutR& out,
                                         const IpmOpts& o, double a_step, double sigmu, double mcw, CarryB& cy, Bnd& r)
     {
         double ll, lu, tl, tu;
@@ -764,7 +786,7 @@ struct Rti {
             r.lnew = 0.0; r.gam = 0.0; r.Gam = 0.0;
             if (first) r.znew = 0.0;
         } else {
-            const double dl = in.lin[(R::DLB + b) * LANES], du_ = in.lin[(R::DUB + b) * LANES];
+            const double dl = w.dl, du_ = w.du;
             if (first) {
                 // cold start (HPIPM INIT_VAR with warm_start = 0): slacks from the bounds with the thr0 projection, lam = mu0 / t
                 double z0 = 0.0, t_l = -dl, t_u = du_;
@@ -774,9 +796,9 @@ struct Rti {
                 } else if (t_u < o.thr0) { t_u = o.thr0; z0 = du_ - o.thr0; }
                 r.znew = z0; tl = t_l; tu = t_u; ll = o.mu0 / t_l; lu = o.mu0 / t_u;
             } else {
-                ll = in.it[(R::LAM + b) * LANES]; lu = in.it[(R::LAM + NB2 + b) * LANES];
-                tl = in.it[(R::T + b) * LANES];   tu = in.it[(R::T + NB2 + b) * LANES];
-                const double mc_l = in.st[(R::MC + b) * LANES], mc_u = in.st[(R::MC + NB2 + b) * LANES];
+                ll = w.ll; lu = w.lu;
+                tl = w.tl; tu = w.tu;
+                const double mc_l = w.mcl, mc_u = w.mcu;
                 const double rd_l = dl - zb + tl, rd_u = -du_ + zb + tu;
                 const double rm_l = ll * tl - o.tau_min + mcw * mc_l - sigmu;
                 const double rm_u = lu * tu - o.tau_min + mcw * mc_u - sigmu;
@@ -812,21 +834,21 @@ struct Rti {
     // the adjoint recursion), new iterate, gradient at the new iterate.  v1 / v2: component j of [B A]' (old multipliers /
     // multiplier step of the successor).  bn: the bounded-component terms (reference states), else nullptr.
     NMPC_HD static double state_component(int k, int j, bool first, double v1, double v2, double H, const Bnd* bn,
-                                          const StageInR& in, const StageOutR& out, double a_step, CarryB& cy, double& gxj)
+                                          const StRows& w, const StageOutR& out, double a_step, CarryB& cy, double& gxj)
     {
         using C = CarryB;
         const bool hasX = k > 0;
         double* sc = cy.sc;
-        const double qx = in.lin[(R::Q + NU + j) * LANES];
+        const double qx = w.q;
         double zx, pin = 0.0, pi_old = 0.0;
         if (first) {
-            zx = hasX ? (bn ? bn->znew : 0.0) : in.it[(R::Z + NU + j) * LANES];
+            zx = hasX ? (bn ? bn->znew : 0.0) : w.z;
             sc[(C::SC_DPI + j) * PSTRIDE] = 0.0;
         } else {
-            zx = in.it[(R::Z + NU + j) * LANES];
+            zx = w.z;
             if (hasX) {
-                const double dzx = in.st[(R::DZ + NU + j) * LANES];
-                pin = in.it[(R::PI + j) * LANES];
+                const double dzx = w.dz;
+                pin = w.pi;
                 pi_old = pin;
                 double r = qx + H * zx - pin + v1 + H * dzx + v2;
                 if (bn) r += bn->ldo - bn->dld;
@@ -857,8 +879,9 @@ struct Rti {
         const double* lti = tb.lti + (hasU ? k : 0) * 4 * NV;
         const double* thr = tb.thr + (hasU ? k : 0) * NC;
         const double* Wk = tb.W + (hasU ? k : 0) * NY;
-        // entry (i, c) of the pose rows of [A | B] (columns theta | actual | ref | u); nothing is linearised at stage N
-#define EL_(i, c) (hasU ? ((i) < R::ER ? in.lin[(R::E + (i) * NC + (c)) * LANES] : thr[c]) : 0.0)
+        // entry (i, c) of the pose rows of [A | B] (columns theta | actual | ref | u), loaded whether or not the stage has it;
+        // nothing is linearised at stage N
+#define EL_(i, c) ((i) < R::ER ? in.lin[(R::E + (i) * NC + (c)) * LANES] : thr[c])
         // pose part of the successor's carries; the successor's state for the dynamics residual
         double p0[3], d0[3], xo[3];
 #pragma unroll
@@ -867,15 +890,21 @@ struct Rti {
         }
         // ---- pose components x, y, theta: unit columns for x and y ---------------------------------------------------------
         double acc[3];                       // pose rows of [A B] z at the new iterate
+        double b0p[3];
         {
-            const double e0 = EL_(0, 0), e1 = EL_(1, 0), e2 = EL_(2, 0);
+            StRows w[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) { load_state_rows(j, first, in, w[j]); b0p[j] = in.lin[(R::B0 + j) * LANES]; }
+            const double l0 = EL_(0, 0), l1 = EL_(1, 0), l2 = EL_(2, 0);
+            NMPC_PHASE_FENCE();
+            const double e0 = hasU ? l0 : 0.0, e1 = hasU ? l1 : 0.0, e2 = hasU ? l2 : 0.0;
             double zp[3];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const double v1 = hasU ? (j < 2 ? p0[j] : e0 * p0[0] + e1 * p0[1] + e2 * p0[2]) : 0.0;
                 const double v2 = hasU ? (j < 2 ? d0[j] : e0 * d0[0] + e1 * d0[1] + e2 * d0[2]) : 0.0;
                 const double H = hasU ? tb.dt * Wk[j] : We[j];
-                zp[j] = state_component(k, j, first, v1, v2, H, nullptr, in, out, a_step, cy, gx[j]);
+                zp[j] = state_component(k, j, first, v1, v2, H, nullptr, w[j], out, a_step, cy, gx[j]);
             }
             acc[0] = zp[0] + e0 * zp[2]; acc[1] = zp[1] + e1 * zp[2]; acc[2] = e2 * zp[2];
 #pragma unroll
@@ -886,6 +915,22 @@ struct Rti {
         for (int c = 0; c < NV; c++) {
             NMPC_PHASE_FENCE();
             const int ja = 3 + c, jr = 3 + NV + c;
+            // every row of the channel, ahead of its arithmetic
+            const int qc = 1 + 2 * NV + c, qa = 1 + c, qr = 1 + NV + c;
+            const double lc0 = EL_(0, qc), lc1 = EL_(1, qc), lc2 = EL_(2, qc);
+            const double la0 = EL_(0, qa), la1 = EL_(1, qa), la2 = EL_(2, qa);
+            const double lr0 = EL_(0, qr), lr1 = EL_(1, qr), lr2 = EL_(2, qr);
+            const double qu = in.lin[(R::Q + c) * LANES];
+            const double zu0 = in.it[(R::Z + c) * LANES];
+            const double dzu0 = first ? 0.0 : in.st[(R::DZ + c) * LANES];
+            BndRows wu, wr;
+            load_bound_rows(c, first, in, wu);
+            load_bound_rows(NV + c, first, in, wr);
+            StRows wa, ws;
+            load_state_rows(ja, first, in, wa);
+            load_state_rows(jr, first, in, ws);
+            const double b0a = in.lin[(R::B0 + ja) * LANES], b0r = in.lin[(R::B0 + jr) * LANES];
+            NMPC_PHASE_FENCE();
             const double pa = sc[(C::SC_PIO + ja) * PSTRIDE], pr = sc[(C::SC_PIO + jr) * PSTRIDE];
             const double da = sc[(C::SC_DPI + ja) * PSTRIDE], dr = sc[(C::SC_DPI + jr) * PSTRIDE];
             const double xa = sc[(C::SC_XN + ja) * PSTRIDE], xr = sc[(C::SC_XN + jr) * PSTRIDE];
@@ -893,16 +938,14 @@ struct Rti {
             // control c
             double zun = 0.0;
             {
-                const int q = 1 + 2 * NV + c;
-                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double e0 = hasU ? lc0 : 0.0, e1 = hasU ? lc1 : 0.0, e2 = hasU ? lc2 : 0.0;
                 const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + au * pa + ru * pr;
                 const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + au * da + ru * dr;
                 const double H = hasU ? tb.dt * Wk[NX + c] : 0.0;
-                const double qu = in.lin[(R::Q + c) * LANES];
-                const double zu = first ? 0.0 : in.it[(R::Z + c) * LANES];
-                const double dzu = (!first && hasU) ? in.st[(R::DZ + c) * LANES] : 0.0;
+                const double zu = first ? 0.0 : zu0;
+                const double dzu = (!first && hasU) ? dzu0 : 0.0;
                 Bnd bn;
-                bound_component(hasU, first, c, zu, dzu, in, out, o, a_step, sigmu, mcw, cy, bn);
+                bound_component(hasU, first, c, zu, dzu, wu, out, o, a_step, sigmu, mcw, cy, bn);
                 if (!first && hasU) {
                     // stationarity residual of the Newton system, control rows (diagnostic: the quantity HPIPM's
                     // iterative refinement would test)
@@ -920,34 +963,32 @@ struct Rti {
             // actual c
             double zan;
             {
-                const int q = 1 + c;
-                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double e0 = hasU ? la0 : 0.0, e1 = hasU ? la1 : 0.0, e2 = hasU ? la2 : 0.0;
                 const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + av * pa;
                 const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + av * da;
                 const double H = hasU ? tb.dt * Wk[ja] : We[ja];
-                zan = state_component(k, ja, first, v1, v2, H, nullptr, in, out, a_step, cy, gx[ja]);
+                zan = state_component(k, ja, first, v1, v2, H, nullptr, wa, out, a_step, cy, gx[ja]);
                 acc[0] += e0 * zan; acc[1] += e1 * zan; acc[2] += e2 * zan;
             }
             // reference c (bounded)
             double zrn;
             {
-                const int q = 1 + NV + c;
-                const double e0 = EL_(0, q), e1 = EL_(1, q), e2 = EL_(2, q);
+                const double e0 = hasU ? lr0 : 0.0, e1 = hasU ? lr1 : 0.0, e2 = hasU ? lr2 : 0.0;
                 const double v1 = e0 * p0[0] + e1 * p0[1] + e2 * p0[2] + ar * pa + pr;
                 const double v2 = e0 * d0[0] + e1 * d0[1] + e2 * d0[2] + ar * da + dr;
                 const double H = hasU ? tb.dt * Wk[jr] : We[jr];
-                const double zr = (first || !hasX) ? 0.0 : in.it[(R::Z + NU + jr) * LANES];
-                const double dzr = (first || !hasX) ? 0.0 : in.st[(R::DZ + NU + jr) * LANES];
+                const double zr = (first || !hasX) ? 0.0 : ws.z;
+                const double dzr = (first || !hasX) ? 0.0 : ws.dz;
                 Bnd bn;
-                bound_component(hasX, first, NV + c, zr, dzr, in, out, o, a_step, sigmu, mcw, cy, bn);
-                zrn = state_component(k, jr, first, v1, v2, H, hasX ? &bn : nullptr, in, out, a_step, cy, gx[jr]);
+                bound_component(hasX, first, NV + c, zr, dzr, wr, out, o, a_step, sigmu, mcw, cy, bn);
+                zrn = state_component(k, jr, first, v1, v2, H, hasX ? &bn : nullptr, ws, out, a_step, cy, gx[jr]);
                 Gam[NV + c] = bn.Gam;
                 acc[0] += e0 * zrn; acc[1] += e1 * zrn; acc[2] += e2 * zrn;
             }
             // the channel's two rows of the dynamics residual
             if (hasU) {
-                rb[ja] = av * zan + ar * zrn + au * zun + (in.lin[(R::B0 + ja) * LANES] - xa);
-                rb[jr] = zrn + ru * zun + (in.lin[(R::B0 + jr) * LANES] - xr);
+                rb[ja] = av * zan + ar * zrn + au * zun + (b0a - xa);
+                rb[jr] = zrn + ru * zun + (b0r - xr);
                 cy.nb = fmax(cy.nb, fmax(fabs(rb[ja]), fabs(rb[jr])));
             }
             sc[(C::SC_XN + ja) * PSTRIDE] = zan; sc[(C::SC_XN + jr) * PSTRIDE] = zrn;
@@ -955,7 +996,7 @@ struct Rti {
         if (hasU) {
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                rb[i] = acc[i] + (in.lin[(R::B0 + i) * LANES] - xo[i]);
+                rb[i] = acc[i] + (b0p[i] - xo[i]);
                 cy.nb = fmax(cy.nb, fabs(rb[i]));
             }
         }
@@ -1138,7 +1179,9 @@ struct Rti {
             dlb_[b] = in.lin[(R::DLB + b) * LANES]; dub_[b] = in.lin[(R::DUB + b) * LANES];
             if (delta) { mcl_[b] = in.st[(R::MC + b) * LANES]; mcu_[b] = in.st[(R::MC + NB2 + b) * LANES]; }
         };
-        constexpr bool HOIST = !LEAN;          // four channels: 72 values do not fit the 128 registers of the solve sweeps
+        // two channels: all rows at the top of the stage; four channels (72 values against the 128 registers of the solve
+        // sweeps): the control rows and the reference-state rows as two groups, each ahead of its own arithmetic
+        constexpr bool HOIST = !LEAN;
         if (HOIST) {
 #pragma unroll
             for (int b = 0; b < NB2; b++) load_rows(b);
@@ -1162,8 +1205,11 @@ struct Rti {
 #pragma unroll
         for (int b = 0; b < NB2; b++) {
             const bool act = (b < NV) ? hasU : hasX;
+            if (!HOIST && (b == 0 || b == NV)) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) load_rows(b + q);
+            }
             if (act) {
-                if (!HOIST) load_rows(b);
                 const double ll = ll_[b], lu = lu_[b];
                 const double tl = tl_[b], tu = tu_[b];
                 const double zb = zb_[b];
@@ -1216,9 +1262,14 @@ struct Rti {
             mcl_[b] = in.st[(R::MC + b) * LANES]; mcu_[b] = in.st[(R::MC + NB2 + b) * LANES];
         };
         constexpr bool HOIST = !LEAN;
+        double luu_[NLU], kh_[NV * NX];
         if (HOIST) {
 #pragma unroll
             for (int b = 0; b < NB2; b++) load_rows(b);
+#pragma unroll
+            for (int i = 0; i < NLU; i++) luu_[i] = in.fa[(R::LUU + i) * LANES];
+#pragma unroll
+            for (int i = 0; i < NV * NX; i++) kh_[i] = in.fa[(R::KH + i) * LANES];
         }
         double qu[NV], qx[NX];
 #pragma unroll
@@ -1233,8 +1284,11 @@ struct Rti {
 #pragma unroll
         for (int b = 0; b < NB2; b++) {
             const bool act = (b < NV) ? hasU : hasX;
+            if (!HOIST && (b == 0 || b == NV)) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) load_rows(b + q);
+            }
             if (act) {
-                if (!HOIST) load_rows(b);
                 const double tl = tl_[b], tu = tu_[b];
                 const double g = (mcw * mcl_[b] - sigmu) / tl - (mcw * mcu_[b] - sigmu) / tu;
                 if (b < NV) qu[b] += g; else qx[3 + b] += g;
@@ -1246,8 +1300,8 @@ struct Rti {
             for (int a = 0; a < NV; a++) {
                 double s = qu[a];
 #pragma unroll
-                for (int c = 0; c < a; c++) s -= in.fa[(R::LUU + a * (a + 1) / 2 + c) * LANES] * lh[c];
-                lh[a] = s * in.fa[(R::LUU + a * (a + 1) / 2 + a) * LANES];
+                for (int c = 0; c < a; c++) s -= (HOIST ? luu_[a * (a + 1) / 2 + c] : in.fa[(R::LUU + a * (a + 1) / 2 + c) * LANES]) * lh[c];
+                lh[a] = s * (HOIST ? luu_[a * (a + 1) / 2 + a] : in.fa[(R::LUU + a * (a + 1) / 2 + a) * LANES]);
                 out.fa[(R::LHD + a) * LANES] = lh[a];
             }
             if (hasX) {
@@ -1255,7 +1309,7 @@ struct Rti {
                 for (int j = 0; j < NX; j++) {
                     double s = qx[j];
 #pragma unroll
-                    for (int a = 0; a < NV; a++) s -= in.fa[(R::KH + a * NX + j) * LANES] * lh[a];
+                    for (int a = 0; a < NV; a++) s -= (HOIST ? kh_[a * NX + j] : in.fa[(R::KH + a * NX + j) * LANES]) * lh[a];
                     cy.dp[j] = s;
                 }
             }

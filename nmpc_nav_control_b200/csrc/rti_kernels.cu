@@ -874,6 +874,7 @@ extern "C" int nmpc_create(int model, int max_batch, int device, nmpc_solver** o
     if (const char* e = getenv("NMPC_SOLO_MAX")) { int v = atoi(e); if (v >= 0) s->solo_max = v; }
     if (const char* e = getenv("NMPC_HYB_KMAX")) { int v = atoi(e); if (v >= 0 && v <= 1000) s->hyb_kmax = v; }
     if (const char* e = getenv("NMPC_HYB_MIN")) { int v = atoi(e); if (v >= 0) s->hyb_min = v; }
+    if (model == 1) s->hyb_frac = 0.6;     // omni4: 103.4 ms per 65,536 instances against 104.9 at 0.75 (tools/gpu/sweep_frac.sh)
     if (const char* e = getenv("NMPC_HYB_FRAC")) { double v = atof(e); if (v >= 0.0 && v <= 1.0) s->hyb_frac = v; }
     {
         s->ws_doubles_per_inst = s->tile_doubles / LANES;
