@@ -12,5 +12,5 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_ip
 timeout 900 ncu --metrics $M --clock-control none -k regex:^k_ -c 45 --csv --log-file gpurun_out/r02_launches_omni4_$TAG.csv python tools/bench_models.py --latency-calls 0 --batches omni4:65536 > gpurun_out/ncu_omni.log 2>&1
 timeout 1200 python tools/bench_models.py --latency-calls 1000 --batches diff:1,diff:148,diff:592,diff:1024,diff:4096,diff:16384,diff:65536,diff:131072,tric:148,tric:65536,omni4:65536 > gpurun_out/r02_models_$TAG.jsonl 2> gpurun_out/r02_models_$TAG.err; tail -4 gpurun_out/r02_models_$TAG.jsonl | cut -c1-200
 timeout 600 python tools/bench_models.py --ctrl diff:65536,tric:65536,omni4:65536,diff:1 > gpurun_out/r02_ctrl_$TAG.jsonl 2> gpurun_out/r02_ctrl_$TAG.err; cut -c1-200 gpurun_out/r02_ctrl_$TAG.jsonl
-NMPC_B200_LIB=$PWD/build/var/lib_soloprof.so timeout 120 python tools/solo_prof.py diff > gpurun_out/r02_solo_phase_cycles_$TAG.txt 2>&1
+[ -f build/var/lib_soloprof.so ] && NMPC_B200_LIB=$PWD/build/var/lib_soloprof.so timeout 120 python tools/solo_prof.py diff > gpurun_out/r02_solo_phase_cycles_$TAG.txt 2>&1
 ls -la gpurun_out | tail -12
