@@ -543,7 +543,7 @@ struct Rti {
     template <bool IMAGE = false>
     NMPC_HD static void stage_B_update_whole(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
                                        const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy,
-                                       double* gu, double* gx, double* rb, double* Gam)
+                                       double* gu, double* gx, double* rb, double* Gam, L* lin_keep = nullptr)
     {
         using C = CarryB;
         const bool hasU = k < NSTAGE, hasX = k > 0;
@@ -565,7 +565,8 @@ struct Rti {
         // Rows that a stage does not have (controls of stage N, states of stage 0) exist in the tile; what is read there is
         // discarded by the selects below.
         const int kt = hasU ? k : 0;                                   // the tables have N rows
-        L lin;
+        L lin_local;
+        L& lin = lin_keep ? *lin_keep : lin_local;
         load_lin(in.lin, tb.lti + kt * 4 * NV, tb.thr + kt * NC, lin);
         double b0[NX];
 #pragma unroll
@@ -1014,7 +1015,8 @@ struct Rti {
     // phase 2 of a B stage: one step of the Riccati recursion.
     // reads : LIN[E]      writes: FA[LUU,KH,LH,RB]
     NMPC_HD static void stage_B_riccati(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
-                                        const IpmOpts& o, CarryB& cy, double* gu, double* gx, const double* rb, const double* Gam)
+                                        const IpmOpts& o, CarryB& cy, double* gu, double* gx, const double* rb, const double* Gam,
+                                        const L* lin_kept = nullptr)
     {
         using C = CarryB;
         const bool hasU = k < NSTAGE, hasX = k > 0;
@@ -1023,7 +1025,8 @@ struct Rti {
         double* Pn = sc + (size_t)C::SC_P * PSTRIDE;              // ... overwritten in place by this stage's
         if (hasU) {
             typename LinSel<LEAN>::type lin;
-            load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
+            if (!LEAN && lin_kept) lin = *reinterpret_cast<const typename LinSel<LEAN>::type*>(lin_kept);   // the update half's view, kept in registers
+            else load_lin(in.lin, tb.lti + k * 4 * NV, tb.thr + k * NC, lin);
 #pragma unroll
             for (int i = 0; i < NX; i++) out.fa[(R::RB + i) * LANES] = rb[i];
             {
@@ -1146,6 +1149,15 @@ struct Rti {
                                 const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy)
     {
         double gu[NV], gx[NX], rb[NX], Gam[NB2];
+#if defined(__CUDA_ARCH__) && NMPC_B_KEEP_LIN
+        if (!LEAN) {
+            L lin;                        // the rows of [A B] stay in registers from the update half to the Riccati half
+            stage_B_update_whole<false>(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam, &lin);
+            NMPC_PHASE_FENCE();
+            stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam, &lin);
+            return;
+        }
+#endif
         stage_B_update(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
         NMPC_PHASE_FENCE();
         stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam);
@@ -1512,10 +1524,11 @@ struct Rti {
                     const StageOut out = tile_stage_out<R>(tile_lane, k);
                     in.st = img;
                     double gu[NV], gx[NX], rb[NX], Gam[NB2];
-                    stage_B_update_whole<true>(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy, gu, gx, rb, Gam);
+                    L lin;
+                    stage_B_update_whole<true>(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy, gu, gx, rb, Gam, NMPC_B_KEEP_LIN ? &lin : nullptr);
                     NMPC_PHASE_FENCE();
                     if (k > 0) fetch(k - 1);
-                    stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam);
+                    stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam, NMPC_B_KEEP_LIN ? &lin : nullptr);
                 }
             } else
 #endif
