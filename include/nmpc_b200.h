@@ -127,7 +127,9 @@ int nmpc_sqp_solve_device(nmpc_solver* s, int B, const double* d_x0bar, const do
 /* ---- host-buffer call (what a controller process would bind): instance-major host arrays ---
  *   x0bar [B][nx], yref [B][N+1][nyref], We [B][nx] or NULL   -> copied H2D and transposed on device
  *   u0 [B][nu], x1 [B][nx], status [B], qp_iter [B]            <- copied D2H (what run() reads, Diff.cpp:151-169)
- * Uses and updates the solver's persisted iterate.  Synchronous. */
+ * Uses and updates the solver's persisted iterate.  Synchronous.  Calls with at most 64 instances (the ROS drop-in's one
+ * robot per call, NMPCNavControlDiff.cpp:96-169) go through one pinned staging buffer with ONE copy each way; the results are
+ * the same bits as the general path's. */
 int nmpc_rti_solve_host(nmpc_solver* s, int B, const double* x0bar, const double* yref, int nyref, const double* We,
                         double* u0, double* x1, int* status, int* qp_iter);
 
