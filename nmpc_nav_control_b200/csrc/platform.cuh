@@ -43,6 +43,9 @@ NMPC_HD void nmpc_sincos(double a, double* s, double* c) {
 #ifndef NMPC_B_STAGE_IMAGE
 #define NMPC_B_STAGE_IMAGE 1            // factorising sweep of diff / tric: iterate and step rows of the next stage copied asynchronously into shared memory
 #endif
+#ifndef NMPC_B_L2_PREFETCH
+#define NMPC_B_L2_PREFETCH 1            // the factorising sweeps prefetch the rows of the next stage into L2 between their two halves
+#endif
 #ifndef NMPC_B_KEEP_LIN
 #define NMPC_B_KEEP_LIN 1               // factorising sweep of diff / tric: the rows of [A B] stay in registers from the update half to the Riccati half
 #endif

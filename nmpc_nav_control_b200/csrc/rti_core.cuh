@@ -1145,6 +1145,20 @@ struct Rti {
         }
     }
 
+#if defined(__CUDA_ARCH__)
+    // nf rows of the stage BELOW the one `rows_k` points at (stage k - 1: one record further down in its group) pulled into L2;
+    // the active lanes of the warp split the 128-byte lines.  Issued between the two halves of a factorising stage, so the
+    // next stage's rows cross HBM while this one's Riccati half computes.
+    __device__ __forceinline__ static void prefetch_rows_prev(const double* rows_k, int nf)
+    {
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & (LANES - 1);
+        const int n = __popc(m), r = __popc(m & ((1u << lane) - 1u));
+        const char* p = reinterpret_cast<const char*>(rows_k - lane - (size_t)nf * LANES);
+        const int lines = nf * (LANES * (int)sizeof(double) / 128);
+        for (int i = r; i < lines; i += n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * 128));
+    }
+#endif
     NMPC_HD static void stage_B(int k, const StageIn& in, const StageOut& out, const Tables& tb, const double* We,
                                 const IpmOpts& o, bool first, double a_step, double sigmu, double mcw, CarryB& cy)
     {
@@ -1154,12 +1168,24 @@ struct Rti {
             L lin;                        // the rows of [A B] stay in registers from the update half to the Riccati half
             stage_B_update_whole<false>(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam, &lin);
             NMPC_PHASE_FENCE();
+#if NMPC_B_L2_PREFETCH
+            if (k > 0) {
+                prefetch_rows_prev(in.lin, R::NF_LIN);
+                if (!first) { prefetch_rows_prev(in.it, R::NF_IT); prefetch_rows_prev(in.st, R::NF_ST); }
+            }
+#endif
             stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam, &lin);
             return;
         }
 #endif
         stage_B_update(k, in, out, tb, We, o, first, a_step, sigmu, mcw, cy, gu, gx, rb, Gam);
         NMPC_PHASE_FENCE();
+#if defined(__CUDA_ARCH__) && NMPC_B_L2_PREFETCH
+        if (k > 0) {
+            prefetch_rows_prev(in.lin, R::NF_LIN);
+            if (!first) { prefetch_rows_prev(in.it, R::NF_IT); prefetch_rows_prev(in.st, R::NF_ST); }
+        }
+#endif
         stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam);
     }
 
@@ -1528,6 +1554,9 @@ struct Rti {
                     stage_B_update_whole<true>(k, in, out, tb, We, o, false, a, c.sigmu, c.mcw, cy, gu, gx, rb, Gam, NMPC_B_KEEP_LIN ? &lin : nullptr);
                     NMPC_PHASE_FENCE();
                     if (k > 0) fetch(k - 1);
+#if NMPC_B_L2_PREFETCH
+                    if (k > 0) { prefetch_rows_prev(in.lin, R::NF_LIN); prefetch_rows_prev(tile_stage_in<R>(tile_lane, k).it, R::NF_IT); }
+#endif
                     stage_B_riccati(k, in, out, tb, We, o, cy, gu, gx, rb, Gam, NMPC_B_KEEP_LIN ? &lin : nullptr);
                 }
             } else
